@@ -1,0 +1,155 @@
+"""ctypes binding of the C ABI (``include/geot_b200.h``) -- the call a non-torch host makes.
+
+Used by the parity tests and by ``bench.py`` so that what is tested and timed is the exported
+``extern "C"`` surface itself; torch tensors only provide device memory and streams here.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import LIB_PATH
+
+F32, F64, BF16, F16 = 0, 1, 2, 3
+SUM, MEAN, MAX, MIN, PROD = 0, 1, 2, 3, 4
+W_NONE, W_EDGE, W_EDGE_HEAD, W_HEAD_EDGE = 0, 1, 2, 3
+REDUCE = {"sum": SUM, "mean": MEAN, "max": MAX, "amax": MAX, "min": MIN, "amin": MIN, "prod": PROD}
+DTYPE = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}
+
+# every symbol include/geot_b200.h declares
+SYMBOLS = [
+    "geot_b200_version", "geot_b200_arch", "geot_b200_status_string", "geot_b200_last_cuda_error",
+    "geot_b200_index_last", "geot_b200_plan_bytes", "geot_b200_format_preprocess", "geot_b200_plan_shards",
+    "geot_b200_workspace_bytes", "geot_b200_segment_reduce", "geot_b200_index_scatter",
+    "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
+    "geot_b200_segment_reduce_host",
+]
+
+
+class GeotPlan(ctypes.Structure):
+    _fields_ = [("E", ctypes.c_int64), ("S", ctypes.c_int64), ("num_segments", ctypes.c_int64),
+                ("max_degree", ctypes.c_int64), ("is_sorted", ctypes.c_int32), ("has_gaps", ctypes.c_int32),
+                ("rowptr", ctypes.c_void_p)]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("geot_b200: %s not built; there is no fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.geot_b200_status_string.restype = ctypes.c_char_p
+        L.geot_b200_last_cuda_error.restype = ctypes.c_char_p
+        L.geot_b200_plan_bytes.restype = ctypes.c_size_t
+        L.geot_b200_plan_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64]
+        L.geot_b200_workspace_bytes.restype = ctypes.c_size_t
+        L.geot_b200_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+        vp, i64, ci, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_size_t
+        L.geot_b200_index_last.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_int64), vp]
+        L.geot_b200_format_preprocess.argtypes = [vp, i64, i64, vp, sz, ctypes.POINTER(GeotPlan), vp]
+        L.geot_b200_plan_shards.argtypes = [ctypes.POINTER(GeotPlan), ci, ctypes.POINTER(ctypes.c_int64),
+                                            ctypes.POINTER(ctypes.c_int64), vp]
+        L.geot_b200_segment_reduce.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci,
+                                               ctypes.POINTER(GeotPlan), vp, sz, vp]
+        L.geot_b200_index_scatter.argtypes = [vp, vp, vp, i64, i64, i64, ci, ci, ci, ctypes.POINTER(GeotPlan), vp, sz, vp]
+        L.geot_b200_gather_scatter.argtypes = [vp, vp, vp, vp, i64, i64, i64, ci, ci, ctypes.POINTER(GeotPlan), vp, sz, vp]
+        L.geot_b200_gather_weight_scatter.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, ci,
+                                                      ctypes.POINTER(GeotPlan), vp, sz, vp]
+        L.geot_b200_mh_spmm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci,
+                                        ctypes.POINTER(GeotPlan), vp, sz, vp]
+        L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
+        _lib = L
+    return _lib
+
+
+class AbiError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        L = lib()
+        msg = L.geot_b200_status_string(status).decode()
+        if status == 4:
+            msg += ": " + L.geot_b200_last_cuda_error().decode()
+        raise AbiError("geot_b200 %s failed: %s (status %d)" % (what, msg, status))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DevicePlan:
+    """format_preprocess through the C ABI; owns its device buffer."""
+
+    def __init__(self, dst_index: torch.Tensor, S: int = None):
+        L = lib()
+        E = dst_index.numel()
+        if S is None:
+            last = ctypes.c_int64(-1)
+            check(L.geot_b200_index_last(_ptr(dst_index), E, ctypes.byref(last), _stream()), "index_last")
+            S = last.value + 1
+        nbytes = L.geot_b200_plan_bytes(E, S)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dst_index.device)
+        self.c = GeotPlan()
+        check(L.geot_b200_format_preprocess(_ptr(dst_index), E, S, _ptr(self.buf), nbytes,
+                                            ctypes.byref(self.c), _stream()), "format_preprocess")
+        self.S = S
+        self.rowptr = self.buf[: (S + 1) * 8].view(torch.int64)
+
+    def shards(self, parts: int):
+        rb = (ctypes.c_int64 * (parts + 1))()
+        eb = (ctypes.c_int64 * (parts + 1))()
+        check(lib().geot_b200_plan_shards(ctypes.byref(self.c), parts, rb, eb, _stream()), "plan_shards")
+        return list(rb), list(eb)
+
+
+class Workspace:
+    def __init__(self, E, W, dtype, device, sorted=True):
+        n = lib().geot_b200_workspace_bytes(E, W, DTYPE[dtype], 1 if sorted else 0)
+        self.buf = torch.empty(n, dtype=torch.uint8, device=device)
+        self.nbytes = n
+
+
+def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H=1, weight_layout=None,
+                   sorted=True, plan: DevicePlan = None, out=None, workspace: Workspace = None):
+    """Device-pointer call of geot_b200_segment_reduce.  Returns dst [S, W]."""
+    E = dst_index.numel()
+    W = src.numel() // src.shape[0]
+    F = W // H
+    if S is None:
+        S = plan.S if plan is not None else int(dst_index.max()) + 1
+    if weight_layout is None:
+        weight_layout = W_NONE if weight is None else (W_EDGE if weight.dim() == 1 else W_EDGE_HEAD)
+    if out is None:
+        out = torch.empty([S] + list(src.shape[1:]), dtype=src.dtype, device=src.device)
+    if workspace is None:
+        workspace = Workspace(E, W, src.dtype, src.device, sorted)
+    st = lib().geot_b200_segment_reduce(
+        _ptr(src), _ptr(src_index), _ptr(dst_index), _ptr(weight), _ptr(out), E, S, H, F, DTYPE[src.dtype],
+        REDUCE[reduce], weight_layout, 1 if sorted else 0, ctypes.byref(plan.c) if plan is not None else None,
+        _ptr(workspace.buf), workspace.nbytes, _stream())
+    check(st, "segment_reduce")
+    return out
+
+
+def segment_reduce_host(src, src_index, dst_index, weight, reduce="sum", *, S, H=1, weight_layout=None, out=None):
+    """Host-buffer call (geot_b200_segment_reduce_host): CPU tensors in, CPU tensor out."""
+    E = dst_index.numel()
+    W = src.numel() // src.shape[0]
+    F = W // H
+    if weight_layout is None:
+        weight_layout = W_NONE if weight is None else (W_EDGE if weight.dim() == 1 else W_EDGE_HEAD)
+    if out is None:
+        out = torch.empty([S] + list(src.shape[1:]), dtype=src.dtype)
+    st = lib().geot_b200_segment_reduce_host(_ptr(src), src.shape[0], _ptr(src_index), _ptr(dst_index), _ptr(weight),
+                                            _ptr(out), E, S, H, F, DTYPE[src.dtype], REDUCE[reduce], weight_layout)
+    check(st, "segment_reduce_host")
+    return out

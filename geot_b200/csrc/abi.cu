@@ -1,0 +1,472 @@
+// abi.cu -- the extern "C" boundary declared in include/geot_b200.h: argument checking, kernel shape
+// selection (replaces the reference's decision trees, csrc/cuda/wrapper/*_rule.h), format_preprocess
+// and the host-buffer entry.  No torch / ATen types here; the torch bindings (bindings.cpp) and any
+// other host (ctypes, cgo, JNI) call these functions.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "../../include/geot_b200.h"
+#include "kernels/launch.h"
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e, const char *what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return GEOT_ERR_CUDA;
+}
+#define CUDA_TRY(expr)                                    \
+  do {                                                    \
+    cudaError_t e__ = (expr);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+  } while (0)
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline size_t dtype_size(int dt) { return dt == GEOT_F64 ? 8 : (dt == GEOT_F32 ? 4 : 2); }
+inline size_t acc_size(int dt) { return dt == GEOT_F64 ? 8 : 4; }
+inline int pow2ceil(int64_t x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// ---- kernel shape + edge partition --------------------------------------------------------------
+struct Config {
+  geot::Shape shape;
+  int chunk_edges;
+  int64_t tile_edges;
+  int64_t n_tiles;
+};
+
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+// `vector_ok`: rows are 16-byte addressable (per-head width multiple of the vector width and
+// 16-byte aligned base pointers); otherwise the element-wise kernels are used.
+Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok) {
+  Config c;
+  const int full = (int)(16 / dtype_size(dtype));
+  const int vecw = (vector_ok && F % full == 0) ? full : 1;
+  const int64_t nvec = (W + vecw - 1) / vecw;
+  int lpr, vpl;
+  if (nvec <= 32) {
+    lpr = pow2ceil(nvec);
+    vpl = 1;
+  } else {
+    lpr = 32;
+    vpl = nvec <= 64 ? 2 : 4;
+  }
+  c.shape.vecw = vecw;
+  c.shape.lpr = lpr;
+  c.shape.vpl = vpl;
+  c.shape.col_tiles = (int)((nvec + (int64_t)lpr * vpl - 1) / ((int64_t)lpr * vpl));
+  const int ng = geot::kThreads / lpr;
+  // Edge-count partition: every group owns `chunk` consecutive edges.  Longer chunks amortise the
+  // per-chunk carry handling; shorter ones keep small inputs spread over all 148 SMs.
+  int chunk = env_int("GEOT_B200_CHUNK", 0);
+  if (chunk <= 0) {
+    chunk = 64;
+    while (chunk > 8 && (E + (int64_t)ng * chunk - 1) / ((int64_t)ng * chunk) < 4 * 148) chunk >>= 1;
+  }
+  c.chunk_edges = chunk;
+  c.tile_edges = (int64_t)ng * chunk;
+  c.n_tiles = (E + c.tile_edges - 1) / c.tile_edges;
+  return c;
+}
+
+struct Workspace {
+  void *carry_head, *carry_tail;
+  long long *head_cnt, *tail_cnt;
+  int64_t *tail_row;
+  unsigned char *flags;
+  size_t bytes;
+};
+
+Workspace carve(void *base, int64_t n_tiles, int64_t W, int dtype) {
+  Workspace w;
+  char *p = static_cast<char *>(base);
+  size_t off = 0;
+  const size_t carry = align256((size_t)n_tiles * (size_t)W * acc_size(dtype));
+  w.carry_head = p + off; off += carry;
+  w.carry_tail = p + off; off += carry;
+  w.head_cnt = reinterpret_cast<long long *>(p + off); off += align256((size_t)n_tiles * 8);
+  w.tail_cnt = reinterpret_cast<long long *>(p + off); off += align256((size_t)n_tiles * 8);
+  w.tail_row = reinterpret_cast<int64_t *>(p + off); off += align256((size_t)n_tiles * 8);
+  w.flags = reinterpret_cast<unsigned char *>(p + off); off += align256((size_t)n_tiles + 1);
+  w.bytes = off;
+  return w;
+}
+
+geot::launch_fn pick_launcher(int dtype, int reduce) {
+  using namespace geot;
+  const int r = (reduce == GEOT_MEAN) ? GEOT_SUM : reduce;
+#define ROW(TN) \
+  switch (r) { case 0: return launch_##TN##_0; case 2: return launch_##TN##_2; \
+               case 3: return launch_##TN##_3; case 4: return launch_##TN##_4; } break;
+  switch (dtype) {
+    case GEOT_F32: ROW(f32)
+    case GEOT_F64: ROW(f64)
+    case GEOT_BF16: ROW(bf16)
+    case GEOT_F16: ROW(f16)
+  }
+#undef ROW
+  return nullptr;
+}
+
+// ---- format_preprocess kernels --------------------------------------------------------------------
+struct PlanStats {
+  long long num_segments;
+  long long max_degree;
+  int unsorted;
+  int pad;
+};
+
+// rowptr[r] = first edge position with dst_index >= r  (lower bound; r = 0..S)
+__global__ void rowptr_kernel(const int64_t *__restrict__ idx, int64_t E, int64_t S, int64_t *__restrict__ rowptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > S) return;
+  int64_t lo = 0, hi = E;
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (idx[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  rowptr[r] = lo;
+}
+
+__global__ void index_stats_kernel(const int64_t *__restrict__ idx, int64_t E, PlanStats *stats) {
+  long long heads = 0;
+  int unsorted = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e == 0) { heads += 1; continue; }
+    const int64_t a = idx[e - 1], b = idx[e];
+    heads += (a != b);
+    unsorted |= (b < a);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    heads += __shfl_xor_sync(0xffffffffu, heads, o);
+    unsorted |= __shfl_xor_sync(0xffffffffu, unsorted, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (heads) atomicAdd(reinterpret_cast<unsigned long long *>(&stats->num_segments), (unsigned long long)heads);
+    if (unsorted) atomicOr(&stats->unsorted, 1);
+  }
+}
+
+__global__ void degree_stats_kernel(const int64_t *__restrict__ rowptr, int64_t S, PlanStats *stats) {
+  long long m = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < S; r += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, (long long)(rowptr[r + 1] - rowptr[r]));
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(&stats->max_degree, m);
+}
+
+// shard g starts at the segment boundary nearest to g*E/parts
+__global__ void shard_kernel(const int64_t *__restrict__ rowptr, int64_t S, int64_t E, int parts,
+                             int64_t *row_bounds, int64_t *edge_bounds) {
+  const int g = threadIdx.x;
+  if (g > parts) return;
+  if (g == 0) { row_bounds[0] = 0; edge_bounds[0] = 0; return; }
+  if (g == parts) { row_bounds[g] = S; edge_bounds[g] = E; return; }
+  const int64_t target = (E / parts) * g + ((E % parts) * g) / parts;
+  int64_t lo = 0, hi = S;  // first r with rowptr[r] >= target
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  int64_t r = lo;
+  if (r > 0 && target - rowptr[r - 1] < rowptr[r] - target) r -= 1;
+  row_bounds[g] = r;
+  edge_bounds[g] = rowptr[r];
+}
+
+__global__ void iota_kernel(int64_t *p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+__global__ void gather_index_kernel(const int64_t *__restrict__ perm, const int64_t *__restrict__ in, int64_t *out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[perm[i]];
+}
+
+constexpr int kMaxParts = 64;
+size_t plan_tail_bytes() { return align256(sizeof(PlanStats)) + align256(2 * (kMaxParts + 1) * sizeof(int64_t)); }
+
+int bits_for(int64_t S) { int b = 1; while (b < 63 && ((int64_t)1 << b) < S) ++b; return b; }
+
+}  // namespace
+
+// ==================================================================================================
+extern "C" {
+
+int geot_b200_version(void) { return GEOT_B200_VERSION; }
+int geot_b200_arch(void) { return 100; }
+
+const char *geot_b200_status_string(int s) {
+  switch (s) {
+    case GEOT_OK: return "ok";
+    case GEOT_ERR_INVALID_ARG: return "invalid argument";
+    case GEOT_ERR_UNSUPPORTED: return "unsupported";
+    case GEOT_ERR_WORKSPACE: return "workspace too small or misaligned";
+    case GEOT_ERR_CUDA: return "CUDA error";
+    case GEOT_ERR_EMPTY: return "empty index";
+  }
+  return "unknown status";
+}
+const char *geot_b200_last_cuda_error(void) { return g_cuda_err; }
+
+int geot_b200_index_last(const int64_t *dst_index, int64_t E, int64_t *last, cudaStream_t stream) {
+  if (!dst_index || !last) return GEOT_ERR_INVALID_ARG;
+  if (E <= 0) return GEOT_ERR_EMPTY;
+  CUDA_TRY(cudaMemcpyAsync(last, dst_index + (E - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return GEOT_OK;
+}
+
+size_t geot_b200_plan_bytes(int64_t E, int64_t S) {
+  (void)E;
+  if (S < 0) return 0;
+  return align256((size_t)(S + 1) * sizeof(int64_t)) + plan_tail_bytes();
+}
+
+int geot_b200_format_preprocess(const int64_t *dst_index, int64_t E, int64_t S, void *plan_buf,
+                                size_t plan_bytes, geot_plan_t *plan, cudaStream_t stream) {
+  if (!dst_index || !plan_buf || !plan || S <= 0) return GEOT_ERR_INVALID_ARG;
+  if (E <= 0) return GEOT_ERR_EMPTY;
+  if (plan_bytes < geot_b200_plan_bytes(E, S) || (reinterpret_cast<uintptr_t>(plan_buf) & 255)) return GEOT_ERR_WORKSPACE;
+  int64_t *rowptr = static_cast<int64_t *>(plan_buf);
+  PlanStats *stats = reinterpret_cast<PlanStats *>(static_cast<char *>(plan_buf) + align256((size_t)(S + 1) * 8));
+  CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(PlanStats), stream));
+  const int thr = 256;
+  rowptr_kernel<<<(unsigned)((S + 1 + thr - 1) / thr), thr, 0, stream>>>(dst_index, E, S, rowptr);
+  CUDA_TRY(cudaGetLastError());
+  const unsigned nb = (unsigned)std::min<int64_t>((E + thr - 1) / thr, 148 * 16);
+  index_stats_kernel<<<nb, thr, 0, stream>>>(dst_index, E, stats);
+  CUDA_TRY(cudaGetLastError());
+  const unsigned nb2 = (unsigned)std::min<int64_t>((S + thr - 1) / thr, 148 * 16);
+  degree_stats_kernel<<<nb2, thr, 0, stream>>>(rowptr, S, stats);
+  CUDA_TRY(cudaGetLastError());
+  PlanStats h;
+  CUDA_TRY(cudaMemcpyAsync(&h, stats, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  plan->E = E;
+  plan->S = S;
+  plan->num_segments = h.num_segments;
+  plan->max_degree = h.max_degree;
+  plan->is_sorted = h.unsorted ? 0 : 1;
+  plan->has_gaps = (h.unsorted || h.num_segments < S) ? 1 : 0;
+  plan->rowptr = rowptr;
+  return GEOT_OK;
+}
+
+int geot_b200_plan_shards(const geot_plan_t *plan, int parts, int64_t *row_bounds, int64_t *edge_bounds,
+                          cudaStream_t stream) {
+  if (!plan || !plan->rowptr || !row_bounds || !edge_bounds || parts < 1 || parts > kMaxParts) return GEOT_ERR_INVALID_ARG;
+  char *base = reinterpret_cast<char *>(const_cast<int64_t *>(plan->rowptr));
+  int64_t *d_bounds = reinterpret_cast<int64_t *>(base + align256((size_t)(plan->S + 1) * 8) + align256(sizeof(PlanStats)));
+  shard_kernel<<<1, kMaxParts + 1, 0, stream>>>(plan->rowptr, plan->S, plan->E, parts, d_bounds, d_bounds + (kMaxParts + 1));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(row_bounds, d_bounds, (parts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaMemcpyAsync(edge_bounds, d_bounds + (kMaxParts + 1), (parts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return GEOT_OK;
+}
+
+size_t geot_b200_workspace_bytes(int64_t E, int64_t W, int dtype, int sorted) {
+  if (E <= 0 || W <= 0) return 256;
+  // the vector and the element-wise shapes partition differently: size for the larger
+  size_t best = 0;
+  for (int v = 0; v < 2; ++v) {
+    const Config c = choose_config(E, W, W, dtype, v == 1);
+    Workspace w = carve(nullptr, c.n_tiles, W, dtype);
+    best = std::max(best, w.bytes);
+  }
+  if (sorted) return best;
+  // sorted == 0 additionally needs the sort buffers (keys, permutation, cub scratch)
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int64_t *)nullptr, (int64_t *)nullptr,
+                                  (const int64_t *)nullptr, (int64_t *)nullptr, E);
+  return best + 4 * align256((size_t)E * 8) + align256(cub_bytes);
+}
+
+int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                             const void *weight, void *dst, int64_t E, int64_t S, int64_t H, int64_t F,
+                             int dtype, int reduce, int weight_layout, int sorted, const geot_plan_t *plan,
+                             void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!src || !dst_index || !dst) return GEOT_ERR_INVALID_ARG;
+  if (E <= 0) return GEOT_ERR_EMPTY;
+  if (S <= 0 || H <= 0 || F <= 0) return GEOT_ERR_INVALID_ARG;
+  if (dtype < GEOT_F32 || dtype > GEOT_F16 || reduce < GEOT_SUM || reduce > GEOT_PROD) return GEOT_ERR_INVALID_ARG;
+  if (weight_layout < GEOT_W_NONE || weight_layout > GEOT_W_HEAD_EDGE) return GEOT_ERR_INVALID_ARG;
+  if ((weight_layout == GEOT_W_NONE) != (weight == nullptr)) return GEOT_ERR_INVALID_ARG;
+  if (weight_layout == GEOT_W_EDGE && H != 1) return GEOT_ERR_INVALID_ARG;
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255)) return GEOT_ERR_WORKSPACE;
+  if (plan && (plan->E != E || plan->S > S)) return GEOT_ERR_INVALID_ARG;
+  const int64_t W = H * F;
+  geot::launch_fn launch = pick_launcher(dtype, reduce);
+  if (!launch) return GEOT_ERR_UNSUPPORTED;
+
+  char *ws = static_cast<char *>(workspace);
+  size_t ws_left = workspace_bytes;
+
+  // sorted == 0: sort the edge ids by dst row (stable LSD radix sort keeps the edge order inside a
+  // row), then run the same deterministic kernels with the permutation as an extra gather.  The
+  // reference uses an all-atomic kernel here (index_scatter_kernel.cuh:204-263).
+  const int64_t *d_dst = dst_index, *d_src = src_index;
+  if (!sorted && weight) return GEOT_ERR_UNSUPPORTED;  // weights follow the edge order: sorted input only
+  if (!sorted) {
+    const size_t ebytes = align256((size_t)E * 8);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const int64_t *)nullptr, (int64_t *)nullptr,
+                                    (const int64_t *)nullptr, (int64_t *)nullptr, E);
+    if (ws_left < 4 * ebytes + align256(cub_bytes)) return GEOT_ERR_WORKSPACE;
+    int64_t *keys_out = reinterpret_cast<int64_t *>(ws);
+    int64_t *iota = reinterpret_cast<int64_t *>(ws + ebytes);
+    int64_t *perm = reinterpret_cast<int64_t *>(ws + 2 * ebytes);
+    int64_t *src_perm = reinterpret_cast<int64_t *>(ws + 3 * ebytes);
+    void *cub_tmp = ws + 4 * ebytes;
+    ws += 4 * ebytes + align256(cub_bytes);
+    ws_left -= 4 * ebytes + align256(cub_bytes);
+    const unsigned nb = (unsigned)((E + 255) / 256);
+    iota_kernel<<<nb, 256, 0, stream>>>(iota, E);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, dst_index, keys_out, iota, perm, E, 0, bits_for(S), stream));
+    if (src_index) {
+      gather_index_kernel<<<nb, 256, 0, stream>>>(perm, src_index, src_perm, E);
+      CUDA_TRY(cudaGetLastError());
+      d_src = src_perm;
+    } else {
+      d_src = perm;
+    }
+    d_dst = keys_out;
+    plan = nullptr;
+  }
+
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const Config cfg = choose_config(E, W, F, dtype, aligned);
+  Workspace w = carve(ws, cfg.n_tiles, W, dtype);
+  if (w.bytes > ws_left) return GEOT_ERR_WORKSPACE;
+
+  // Rows that receive no edge must read 0.  The kernels store every non-empty row exactly once and
+  // never touch the others, so dst is cleared first unless the plan proves there is no empty row.
+  const bool need_clear = !(plan && !plan->has_gaps && plan->S == S);
+  if (need_clear) CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)S * (size_t)W * dtype_size(dtype), stream));
+
+  geot::Params p;
+  p.src = src;
+  p.src_index = d_src;
+  p.dst_index = d_dst;
+  p.weight = weight;
+  p.dst = dst;
+  p.E = E;
+  p.W = W;
+  p.F = F;
+  p.per_head_weight = 0;
+  p.ws_e = 1;
+  p.ws_h = 0;
+  if (weight_layout == GEOT_W_EDGE_HEAD) { p.ws_e = H; p.ws_h = 1; p.per_head_weight = (H > 1); }
+  if (weight_layout == GEOT_W_HEAD_EDGE) { p.ws_e = 1; p.ws_h = E; p.per_head_weight = (H > 1); }
+  p.mean = (reduce == GEOT_MEAN);
+  p.chunk_edges = cfg.chunk_edges;
+  p.n_tiles = cfg.n_tiles;
+  p.carry_head = w.carry_head;
+  p.carry_tail = w.carry_tail;
+  p.head_cnt = w.head_cnt;
+  p.tail_cnt = w.tail_cnt;
+  p.tail_row = w.tail_row;
+  p.flags = w.flags;
+  CUDA_TRY(launch(p, cfg.shape, stream));
+  return GEOT_OK;
+}
+
+int geot_b200_index_scatter(const void *src, const int64_t *index, void *dst, int64_t E, int64_t S, int64_t F,
+                            int dtype, int reduce, int sorted, const geot_plan_t *plan, void *workspace,
+                            size_t workspace_bytes, cudaStream_t stream) {
+  return geot_b200_segment_reduce(src, nullptr, index, nullptr, dst, E, S, 1, F, dtype, reduce, GEOT_W_NONE, sorted,
+                                  plan, workspace, workspace_bytes, stream);
+}
+
+int geot_b200_gather_scatter(const void *src, const int64_t *src_index, const int64_t *dst_index, void *dst,
+                             int64_t E, int64_t S, int64_t F, int dtype, int reduce, const geot_plan_t *plan,
+                             void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!src_index) return GEOT_ERR_INVALID_ARG;
+  return geot_b200_segment_reduce(src, src_index, dst_index, nullptr, dst, E, S, 1, F, dtype, reduce, GEOT_W_NONE, 1,
+                                  plan, workspace, workspace_bytes, stream);
+}
+
+int geot_b200_gather_weight_scatter(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                                    const void *weight, void *dst, int64_t E, int64_t S, int64_t F, int dtype,
+                                    int reduce, const geot_plan_t *plan, void *workspace, size_t workspace_bytes,
+                                    cudaStream_t stream) {
+  if (!src_index || !weight) return GEOT_ERR_INVALID_ARG;
+  return geot_b200_segment_reduce(src, src_index, dst_index, weight, dst, E, S, 1, F, dtype, reduce, GEOT_W_EDGE, 1,
+                                  plan, workspace, workspace_bytes, stream);
+}
+
+int geot_b200_mh_spmm(const void *src, const int64_t *src_index, const int64_t *dst_index, const void *weight,
+                      void *dst, int64_t E, int64_t S, int64_t H, int64_t F, int dtype, int reduce, int weight_layout,
+                      const geot_plan_t *plan, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!src_index || !weight) return GEOT_ERR_INVALID_ARG;
+  if (weight_layout != GEOT_W_EDGE_HEAD && weight_layout != GEOT_W_HEAD_EDGE) return GEOT_ERR_INVALID_ARG;
+  return geot_b200_segment_reduce(src, src_index, dst_index, weight, dst, E, S, H, F, dtype, reduce, weight_layout, 1,
+                                  plan, workspace, workspace_bytes, stream);
+}
+
+// ---- host-buffer entry ------------------------------------------------------------------------------
+int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t *src_index,
+                                  const int64_t *dst_index, const void *weight, void *dst, int64_t E, int64_t S,
+                                  int64_t H, int64_t F, int dtype, int reduce, int weight_layout) {
+  if (!src || !dst_index || !dst || N_src <= 0) return GEOT_ERR_INVALID_ARG;
+  if (E <= 0) return GEOT_ERR_EMPTY;
+  if (S <= 0 || H <= 0 || F <= 0 || dtype < GEOT_F32 || dtype > GEOT_F16) return GEOT_ERR_INVALID_ARG;
+  if ((weight_layout == GEOT_W_NONE) != (weight == nullptr)) return GEOT_ERR_INVALID_ARG;
+  const int64_t W = H * F;
+  const size_t es = dtype_size(dtype);
+  const size_t src_rows = src_index ? (size_t)N_src : (size_t)E;
+  const size_t b_src = src_rows * W * es, b_idx = (size_t)E * 8, b_dst = (size_t)S * W * es;
+  const size_t b_w = weight ? (size_t)E * (weight_layout == GEOT_W_EDGE ? 1 : H) * es : 0;
+  const size_t b_ws = geot_b200_workspace_bytes(E, W, dtype, 1);
+  char *d_base = nullptr;
+  const size_t total = align256(b_src) + 2 * align256(b_idx) + align256(b_w) + align256(b_dst) + align256(b_ws);
+  cudaStream_t st = nullptr, st2 = nullptr;
+  cudaEvent_t ev = nullptr;
+  int rc = GEOT_OK;
+#define HOST_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #expr); goto done; } } while (0)
+  {
+    HOST_TRY(cudaMalloc(&d_base, total));
+    HOST_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    HOST_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    HOST_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    char *p = d_base;
+    void *d_src = p; p += align256(b_src);
+    int64_t *d_di = reinterpret_cast<int64_t *>(p); p += align256(b_idx);
+    int64_t *d_si = reinterpret_cast<int64_t *>(p); p += align256(b_idx);
+    void *d_w = p; p += align256(b_w);
+    void *d_dst = p; p += align256(b_dst);
+    void *d_ws = p;
+    // two copy streams so that both directions of the link and both DMA engines are busy
+    HOST_TRY(cudaMemcpyAsync(d_di, dst_index, b_idx, cudaMemcpyHostToDevice, st));
+    HOST_TRY(cudaMemcpyAsync(d_src, src, b_src, cudaMemcpyHostToDevice, st2));
+    if (src_index) HOST_TRY(cudaMemcpyAsync(d_si, src_index, b_idx, cudaMemcpyHostToDevice, st2));
+    if (weight) HOST_TRY(cudaMemcpyAsync(d_w, weight, b_w, cudaMemcpyHostToDevice, st));
+    HOST_TRY(cudaEventRecord(ev, st2));
+    HOST_TRY(cudaStreamWaitEvent(st, ev, 0));
+    rc = geot_b200_segment_reduce(d_src, src_index ? d_si : nullptr, d_di, weight ? d_w : nullptr, d_dst, E, S, H, F,
+                                  dtype, reduce, weight_layout, 1, nullptr, d_ws, b_ws, st);
+    if (rc != GEOT_OK) goto done;
+    HOST_TRY(cudaMemcpyAsync(dst, d_dst, b_dst, cudaMemcpyDeviceToHost, st));
+    HOST_TRY(cudaStreamSynchronize(st));
+  }
+done:
+#undef HOST_TRY
+  if (ev) cudaEventDestroy(ev);
+  if (st) cudaStreamDestroy(st);
+  if (st2) cudaStreamDestroy(st2);
+  if (d_base) cudaFree(d_base);
+  return rc;
+}
+
+}  // extern "C"

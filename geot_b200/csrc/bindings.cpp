@@ -1,0 +1,298 @@
+// bindings.cpp -- thin torch-extension bindings over the C ABI (include/geot_b200.h).
+//
+// Registers the reference's operator schemas under library `geot` (csrc/index_scatter.cpp:43-47,
+// gather_scatter.cpp:16-17, gather_weight_scatter.cpp:12-14, mh_spmm.cpp:23), CUDA only: there is
+// no CPU implementation and no fallback.  Everything here is tensor <-> pointer translation,
+// output allocation and status -> TORCH_CHECK; the arithmetic lives behind the C ABI.
+//
+// Differences from the reference bindings, on purpose:
+//   * `index[-1].item()` per call (csrc/gather_scatter.cpp:27) is replaced by a cached
+//     format_preprocess plan keyed on the index tensor's storage + version: the first call on a
+//     graph synchronises once, later calls not at all;
+//   * the output is allocated uninitialised (the kernels own every row) instead of torch::zeros;
+//   * kernels run on the current stream under a device guard, not on the legacy default stream;
+//   * `reduce` and `dim` are honoured (the reference validates and then ignores both).
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/library.h>
+
+#include <list>
+#include <mutex>
+#include <string>
+#include <tuple>
+
+#include "../../include/geot_b200.h"
+
+namespace {
+
+// ---- helpers ------------------------------------------------------------------------------------
+// Same accepted strings and message as csrc/reduceutils.h:5-22.
+int reduce_enum(c10::string_view reduce) {
+  if (reduce == "max" || reduce == "amax") return GEOT_MAX;
+  if (reduce == "mean") return GEOT_MEAN;
+  if (reduce == "min" || reduce == "amin") return GEOT_MIN;
+  if (reduce == "sum") return GEOT_SUM;
+  if (reduce == "prod") return GEOT_PROD;
+  TORCH_CHECK(false, "reduce argument must be either sum, prod, mean, amax or amin, got ", reduce);
+}
+
+int dtype_enum(const at::Tensor &t) {
+  switch (t.scalar_type()) {
+    case at::kFloat: return GEOT_F32;
+    case at::kDouble: return GEOT_F64;
+    case at::kBFloat16: return GEOT_BF16;
+    case at::kHalf: return GEOT_F16;
+    default: TORCH_CHECK(false, "geot: unsupported dtype ", t.scalar_type(), " (float32, float64, bfloat16, float16)");
+  }
+}
+
+void check_status(int st, const char *what) {
+  if (st == GEOT_OK) return;
+  if (st == GEOT_ERR_CUDA) TORCH_CHECK(false, "geot::", what, ": ", geot_b200_last_cuda_error());
+  if (st == GEOT_ERR_EMPTY) TORCH_CHECK(false, "geot::", what, ": index is empty (the output size is index[-1] + 1)");
+  TORCH_CHECK(false, "geot::", what, ": ", geot_b200_status_string(st));
+}
+
+void check_index(const at::Tensor &idx, const char *name) {
+  TORCH_CHECK(idx.is_cuda(), "geot: ", name, " must be a CUDA tensor (this build has no CPU path)");
+  TORCH_CHECK(idx.scalar_type() == at::kLong, "geot: ", name, " must be int64");
+}
+
+// ---- plan cache -----------------------------------------------------------------------------------
+// Keyed on (storage, offset, numel, version counter): a hit proves the bytes are the ones the plan
+// was built from (the storage is still alive, so its address was not reused, and no in-place torch op
+// touched it).  Small LRU; entries hold the plan's device buffer, not the index tensor.
+struct PlanEntry {
+  explicit PlanEntry(c10::weak_intrusive_ptr<c10::StorageImpl> s) : storage(std::move(s)) {}
+  c10::weak_intrusive_ptr<c10::StorageImpl> storage;
+  const void *storage_raw;
+  int64_t offset, numel;
+  uint32_t version;
+  int device;
+  at::Tensor buf;
+  geot_plan_t plan;
+};
+std::mutex g_plan_mu;
+std::list<PlanEntry> g_plans;
+constexpr size_t kMaxPlans = 16;
+
+uint32_t version_of(const at::Tensor &t) {
+  return t.is_inference() ? 0u : t.unsafeGetTensorImpl()->version_counter().current_version();
+}
+
+// Returns a copy of the cached plan for dst_index (building it on a miss: one stream sync).
+geot_plan_t get_plan(const at::Tensor &dst_index, at::Tensor *keepalive) {
+  c10::StorageImpl *raw = dst_index.storage().unsafeGetStorageImpl();
+  const int64_t off = dst_index.storage_offset(), n = dst_index.numel();
+  const uint32_t ver = version_of(dst_index);
+  const int dev = dst_index.get_device();
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
+      if (it->storage_raw == raw && it->offset == off && it->numel == n && it->version == ver && it->device == dev &&
+          !it->storage.expired()) {
+        g_plans.splice(g_plans.begin(), g_plans, it);
+        *keepalive = it->buf;
+        return it->plan;
+      }
+    }
+  }
+  auto stream = at::cuda::getCurrentCUDAStream();
+  int64_t last = -1;
+  check_status(geot_b200_index_last(dst_index.data_ptr<int64_t>(), n, &last, stream), "format_preprocess");
+  TORCH_CHECK(last >= 0, "geot: negative index");
+  const int64_t S = last + 1;
+  const size_t bytes = geot_b200_plan_bytes(n, S);
+  PlanEntry e(dst_index.storage().getWeakStorageImpl());
+  e.buf = at::empty({(int64_t)bytes}, dst_index.options().dtype(at::kByte));
+  check_status(geot_b200_format_preprocess(dst_index.data_ptr<int64_t>(), n, S, e.buf.data_ptr(), bytes, &e.plan, stream),
+               "format_preprocess");
+  e.storage_raw = raw;
+  e.offset = off;
+  e.numel = n;
+  e.version = ver;
+  e.device = dev;
+  *keepalive = e.buf;
+  geot_plan_t plan = e.plan;
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    g_plans.push_front(std::move(e));
+    while (g_plans.size() > kMaxPlans) g_plans.pop_back();
+  }
+  return plan;
+}
+
+void clear_plan_cache() {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_plans.clear();
+}
+
+// ---- the one call every op funnels into ---------------------------------------------------------------
+at::Tensor run(const char *what, const at::Tensor &src_in, const c10::optional<at::Tensor> &src_index_in,
+               const at::Tensor &dst_index_in, const c10::optional<at::Tensor> &weight_in, int64_t H, int64_t F,
+               int reduce, int weight_layout, bool sorted, std::vector<int64_t> out_shape) {
+  c10::cuda::CUDAGuard guard(src_in.device());
+  TORCH_CHECK(src_in.is_cuda(), "geot::", what, ": src must be a CUDA tensor (this build has no CPU path)");
+  check_index(dst_index_in, "index");
+  const at::Tensor src = src_in.contiguous();
+  const at::Tensor dst_index = dst_index_in.contiguous();
+  at::Tensor src_index, weight;
+  if (src_index_in.has_value()) {
+    check_index(*src_index_in, "src_index");
+    src_index = src_index_in->contiguous();
+    TORCH_CHECK(src_index.numel() == dst_index.numel(), "geot::", what, ": src_index and dst_index must have the same length");
+  }
+  if (weight_in.has_value()) {
+    TORCH_CHECK(weight_in->scalar_type() == src.scalar_type(), "geot::", what, ": weight and src must have the same dtype");
+    TORCH_CHECK(weight_in->device() == src.device(), "geot::", what, ": weight and src must be on the same device");
+    weight = weight_in->contiguous();
+  }
+  TORCH_CHECK(dst_index.device() == src.device(), "geot::", what, ": index and src must be on the same device");
+  const int64_t E = dst_index.numel();
+  TORCH_CHECK(E > 0, "geot::", what, ": index is empty (the output size is index[-1] + 1)");
+  const int dtype = dtype_enum(src);
+  auto stream = at::cuda::getCurrentCUDAStream();
+
+  geot_plan_t plan;
+  const geot_plan_t *plan_ptr = nullptr;
+  at::Tensor plan_buf;
+  int64_t S;
+  if (sorted) {
+    plan = get_plan(dst_index, &plan_buf);
+    TORCH_CHECK(plan.is_sorted, "geot::", what, ": index is not sorted (pass sorted=False to index_scatter)");
+    plan_ptr = &plan;
+    S = plan.S;
+  } else {
+    S = dst_index.max().item<int64_t>() + 1;
+  }
+  out_shape[0] = S;
+  at::Tensor out = at::empty(out_shape, src.options());
+  const int64_t W = H * F;
+  const size_t ws_bytes = geot_b200_workspace_bytes(E, W, dtype, sorted ? 1 : 0);
+  at::Tensor ws = at::empty({(int64_t)ws_bytes}, src.options().dtype(at::kByte));
+  const int st = geot_b200_segment_reduce(
+      src.data_ptr(), src_index.defined() ? src_index.data_ptr<int64_t>() : nullptr, dst_index.data_ptr<int64_t>(),
+      weight.defined() ? weight.data_ptr() : nullptr, out.data_ptr(), E, S, H, F, dtype, reduce, weight_layout,
+      sorted ? 1 : 0, plan_ptr, ws.data_ptr(), ws_bytes, stream);
+  check_status(st, what);
+  return out;
+}
+
+// ---- ops ---------------------------------------------------------------------------------------------
+// geot::index_scatter -- csrc/index_scatter.cpp:26-39 + csrc/cuda/index_scatter_cuda.cu:86-105
+at::Tensor index_scatter_cuda_impl(int64_t dim, at::Tensor index, at::Tensor src, c10::string_view reduce, bool sorted) {
+  TORCH_CHECK(dim >= 0 && dim < src.dim(), "dim must be non-negative and less than input dimensions");
+  TORCH_CHECK(index.dim() == 1, "index must be 1 dimensional");
+  TORCH_CHECK(src.size(dim) == index.size(0), "index length must be equal to src dimension size");
+  const int red = reduce_enum(reduce);
+  at::Tensor s = (dim == 0) ? src : src.movedim(dim, 0);
+  s = s.contiguous();
+  const int64_t E = index.size(0);
+  const int64_t F = E > 0 ? s.numel() / E : 0;
+  TORCH_CHECK(F > 0, "geot::index_scatter: src has no elements");
+  at::Tensor out = run("index_scatter", s, c10::nullopt, index, c10::nullopt, 1, F, red, GEOT_W_NONE, sorted, s.sizes().vec());
+  return (dim == 0) ? out : out.movedim(0, dim);
+}
+
+at::Tensor gather_scatter_reduce(at::Tensor src_index, at::Tensor dst_index, at::Tensor src, c10::string_view reduce) {
+  // checks and messages: csrc/cuda/gather_scatter_cuda.cu:18-22
+  TORCH_CHECK(src_index.dim() == dst_index.dim() && src_index.dim() == 1, "src_index and dst_index must be 1 dimensional");
+  TORCH_CHECK(src.dim() == 2, "src must be 2 dimensional");
+  return run("gather_scatter", src, src_index, dst_index, c10::nullopt, 1, src.size(1), reduce_enum(reduce), GEOT_W_NONE, true,
+             src.sizes().vec());
+}
+// geot::gather_scatter_impl -- csrc/gather_scatter.cpp:25-34 (sum)
+at::Tensor gather_scatter_impl(at::Tensor src_index, at::Tensor dst_index, at::Tensor src) {
+  return gather_scatter_reduce(src_index, dst_index, src, "sum");
+}
+
+at::Tensor gather_weight_scatter_reduce(at::Tensor src_index, at::Tensor dst_index, at::Tensor weight, at::Tensor src,
+                                        c10::string_view reduce) {
+  // checks: csrc/cuda/gather_weight_scatter_cuda.cu:27-33
+  TORCH_CHECK(src_index.dim() == dst_index.dim() && src_index.dim() == 1, "src_index and dst_index must be 1 dimensional");
+  TORCH_CHECK(src.dim() == 2, "src must be 2 dimensional");
+  TORCH_CHECK(weight.dim() == 1 && weight.size(0) == dst_index.size(0), "weight must be 1 dimensional with one entry per edge");
+  return run("gather_weight_scatter", src, src_index, dst_index, weight, 1, src.size(1), reduce_enum(reduce), GEOT_W_EDGE, true,
+             src.sizes().vec());
+}
+// geot::gather_weight_scatter_impl -- csrc/gather_weight_scatter.cpp:22-34 (hard-codes "sum", :31)
+at::Tensor gather_weight_scatter_impl(at::Tensor src_index, at::Tensor dst_index, at::Tensor weight, at::Tensor src) {
+  return gather_weight_scatter_reduce(src_index, dst_index, weight, src, "sum");
+}
+
+// geot::mh_spmm -- csrc/mh_spmm.cpp:10-23 + csrc/cuda/mh_spmm_cuda.cu:20-38
+at::Tensor mh_spmm_impl(at::Tensor src_index, at::Tensor dst_index, at::Tensor weight, at::Tensor src, c10::string_view reduce) {
+  TORCH_CHECK(src_index.dim() == dst_index.dim() && src_index.dim() == 1, "src_index and dst_index must be 1 dimensional");
+  TORCH_CHECK(src.dim() == 3, "src must be 3 dimensional");
+  const int red = reduce_enum(reduce);
+  const int64_t E = src_index.size(0), H = src.size(1), F = src.size(2);
+  // weight layout by shape, [E,H] first -- wrapper/mh_spmm_base.h:38-49
+  int layout;
+  if (weight.dim() == 2 && weight.size(0) == E && weight.size(1) == H) layout = GEOT_W_EDGE_HEAD;
+  else if (weight.dim() == 2 && weight.size(1) == E && weight.size(0) == H) layout = GEOT_W_HEAD_EDGE;
+  else throw std::runtime_error("Invalid weight size");
+  return run("mh_spmm", src, src_index, dst_index, weight, H, F, red, layout, true, src.sizes().vec());
+}
+
+// geot::format_preprocess -> (rowptr [S+1] int64 on device, stats [6] int64 on CPU:
+// E, S, num_segments, max_degree, is_sorted, has_gaps)
+std::tuple<at::Tensor, at::Tensor> format_preprocess(at::Tensor dst_index) {
+  check_index(dst_index, "dst_index");
+  TORCH_CHECK(dst_index.dim() == 1, "index must be 1 dimensional");
+  TORCH_CHECK(dst_index.numel() > 0, "geot::format_preprocess: index is empty");
+  c10::cuda::CUDAGuard guard(dst_index.device());
+  at::Tensor idx = dst_index.contiguous();
+  at::Tensor buf;
+  geot_plan_t plan = get_plan(idx, &buf);
+  at::Tensor rowptr = at::from_blob(const_cast<int64_t *>(plan.rowptr), {plan.S + 1},
+                                    [buf](void *) mutable { buf.reset(); }, idx.options());
+  at::Tensor stats = at::empty({6}, at::TensorOptions().dtype(at::kLong));
+  int64_t *s = stats.data_ptr<int64_t>();
+  s[0] = plan.E; s[1] = plan.S; s[2] = plan.num_segments; s[3] = plan.max_degree; s[4] = plan.is_sorted; s[5] = plan.has_gaps;
+  return std::make_tuple(rowptr, stats);
+}
+
+// geot::plan_shards -> CPU int64 [2, parts+1]: row bounds, edge bounds
+at::Tensor plan_shards(at::Tensor dst_index, int64_t parts) {
+  check_index(dst_index, "dst_index");
+  c10::cuda::CUDAGuard guard(dst_index.device());
+  at::Tensor idx = dst_index.contiguous();
+  at::Tensor buf;
+  geot_plan_t plan = get_plan(idx, &buf);
+  TORCH_CHECK(plan.is_sorted, "geot::plan_shards: index is not sorted");
+  at::Tensor out = at::empty({2, parts + 1}, at::TensorOptions().dtype(at::kLong));
+  check_status(geot_b200_plan_shards(&plan, (int)parts, out.data_ptr<int64_t>(), out.data_ptr<int64_t>() + (parts + 1),
+                                     at::cuda::getCurrentCUDAStream()),
+               "plan_shards");
+  return out;
+}
+
+}  // namespace
+
+TORCH_LIBRARY_FRAGMENT(geot, m) {
+  // reference schemas
+  m.def("index_scatter(int dim, Tensor index, Tensor src, str reduce, bool sorted) -> Tensor");
+  m.def("gather_scatter_impl(Tensor src_index, Tensor dst_index, Tensor src) -> Tensor");
+  m.def("gather_weight_scatter_impl(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src) -> Tensor");
+  m.def("mh_spmm(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src, str reduce) -> Tensor");
+  // additions: reduce-aware gather ops, the plan, the multi-GPU partition
+  m.def("gather_scatter_reduce(Tensor src_index, Tensor dst_index, Tensor src, str reduce) -> Tensor");
+  m.def("gather_weight_scatter_reduce(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src, str reduce) -> Tensor");
+  m.def("format_preprocess(Tensor dst_index) -> (Tensor, Tensor)");
+  m.def("plan_shards(Tensor dst_index, int parts) -> Tensor");
+  m.def("clear_plan_cache() -> ()", []() { clear_plan_cache(); });
+  m.def("abi_version() -> int", []() { return (int64_t)geot_b200_version(); });
+}
+
+TORCH_LIBRARY_IMPL(geot, CUDA, m) {
+  m.impl("index_scatter", index_scatter_cuda_impl);
+  m.impl("gather_scatter_impl", gather_scatter_impl);
+  m.impl("gather_weight_scatter_impl", gather_weight_scatter_impl);
+  m.impl("mh_spmm", mh_spmm_impl);
+  m.impl("gather_scatter_reduce", gather_scatter_reduce);
+  m.impl("gather_weight_scatter_reduce", gather_weight_scatter_reduce);
+  m.impl("format_preprocess", format_preprocess);
+  m.impl("plan_shards", plan_shards);
+}

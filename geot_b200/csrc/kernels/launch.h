@@ -1,0 +1,26 @@
+// launch.h -- host-side interface between the C ABI (abi.cu) and the per-(dtype, reduce) kernel
+// translation units (inst.cu compiled once per pair so the build parallelises).
+#pragma once
+#include <cuda_runtime.h>
+#include "segment_reduce.cuh"
+
+namespace geot {
+
+struct Shape {
+  int vecw;       // elements per lane vector (16 bytes worth, or 1 for the unaligned fallback)
+  int lpr;        // lanes per row (group size): power of two <= 32
+  int vpl;        // vectors per lane: 1, 2 or 4 (only with lpr == 32)
+  int col_tiles;  // grid.y: ceil(W / (lpr*vpl*vecw))
+};
+
+typedef cudaError_t (*launch_fn)(const Params &, const Shape &, cudaStream_t);
+
+// defined in inst.cu, one per (dtype, reduce op); index [dtype][red] with red in {sum,max,min,prod}
+#define GEOT_DECL(TN, R) cudaError_t launch_##TN##_##R(const Params &, const Shape &, cudaStream_t);
+GEOT_DECL(f32, 0) GEOT_DECL(f32, 2) GEOT_DECL(f32, 3) GEOT_DECL(f32, 4)
+GEOT_DECL(f64, 0) GEOT_DECL(f64, 2) GEOT_DECL(f64, 3) GEOT_DECL(f64, 4)
+GEOT_DECL(bf16, 0) GEOT_DECL(bf16, 2) GEOT_DECL(bf16, 3) GEOT_DECL(bf16, 4)
+GEOT_DECL(f16, 0) GEOT_DECL(f16, 2) GEOT_DECL(f16, 3) GEOT_DECL(f16, 4)
+#undef GEOT_DECL
+
+}  // namespace geot

@@ -1,0 +1,169 @@
+/*
+ * geot_b200.h -- C ABI of the B200-native (sm_100a) segment-reduction library.
+ *
+ * This is the drop-in boundary for GeoT's hot path: every entry point replaces one host entry point
+ * of the reference's CUDA layer (declared in /root/reference/csrc/cuda/header_cuda.h:4-38) and is
+ * what the reference's torch bindings (csrc/*.cpp) bind after the swap -- see INTEGRATION.md.
+ *
+ *   - plain pointers and sizes only: no ATen / torch types cross this boundary;
+ *   - every function returns a geot_status_t and never throws;
+ *   - all device pointers must belong to the current CUDA device; work is enqueued on `stream`
+ *     (the reference launches on the legacy default stream, gather_scatter_base.h:33; callers
+ *     pass at::cuda::getCurrentCUDAStream());
+ *   - no allocation inside the device entry points: scratch is caller-provided
+ *     (geot_b200_workspace_bytes / geot_b200_plan_bytes);
+ *   - index tensors are int64, as at the reference API (wrapper/gather_scatter_base.h:20-21).
+ *
+ * Semantics:
+ *     dst[dst_index[e], h, :]  (op)=  weight[e, h] * src[src_index[e], h, :]      e = 0 .. E-1
+ * dst has S rows and is fully overwritten; rows that receive no edge are 0.  op in
+ * {sum, mean, max, min, prod}; mean = sum / count; max/min propagate NaN (torch amax/amin).
+ * fp32 and fp64 accumulate in their own type, bf16/fp16 accumulate in fp32 and round once.
+ * The reduction is deterministic (fixed tree, no atomics) for sorted dst_index.
+ */
+#ifndef GEOT_B200_H_
+#define GEOT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+#define GEOT_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define GEOT_API __attribute__((visibility("default")))
+#else
+#define GEOT_API
+#endif
+
+typedef enum {
+  GEOT_OK = 0,
+  GEOT_ERR_INVALID_ARG = 1,  /* null pointer, negative size, bad enum ... */
+  GEOT_ERR_UNSUPPORTED = 2,  /* valid request this build does not implement */
+  GEOT_ERR_WORKSPACE = 3,    /* workspace / plan buffer too small or misaligned */
+  GEOT_ERR_CUDA = 4,         /* a CUDA call failed: see geot_b200_last_cuda_error() */
+  GEOT_ERR_EMPTY = 5         /* E == 0 (the reference raises on index[-1] of an empty tensor) */
+} geot_status_t;
+
+typedef enum { GEOT_F32 = 0, GEOT_F64 = 1, GEOT_BF16 = 2, GEOT_F16 = 3 } geot_dtype_t;
+
+/* Same members as the reference's ReductionType (csrc/reducetype.h:3). */
+typedef enum { GEOT_SUM = 0, GEOT_MEAN = 1, GEOT_MAX = 2, GEOT_MIN = 3, GEOT_PROD = 4 } geot_reduce_t;
+
+/* Where weight element (e, h) lives.  EDGE: weight[e] (gather_weight_scatter_base.h:25);
+ * EDGE_HEAD: weight[e*H + h] (mh_spmm_kernel.cuh:66); HEAD_EDGE: weight[h*E + e] (:168). */
+typedef enum { GEOT_W_NONE = 0, GEOT_W_EDGE = 1, GEOT_W_EDGE_HEAD = 2, GEOT_W_HEAD_EDGE = 3 } geot_weight_layout_t;
+
+/* ---- library queries ------------------------------------------------------------------------ */
+
+GEOT_API int geot_b200_version(void);                 /* GEOT_B200_VERSION */
+GEOT_API int geot_b200_arch(void);                    /* 100: the SASS in this library is sm_100a only */
+GEOT_API const char *geot_b200_status_string(int status);
+GEOT_API const char *geot_b200_last_cuda_error(void); /* text of the last CUDA failure on this thread */
+
+/* ---- format_preprocess: segment pointers + edge-count partition ------------------------------ */
+
+/* Result of geot_b200_format_preprocess.  Host POD; `rowptr` points into the caller's device
+ * plan buffer.  Replaces the reference's per-call `index[-1].item()` (csrc/gather_scatter.cpp:27)
+ * and its decision-tree features (wrapper/gather_scatter_rule.h:9-12) with facts about the graph
+ * that are computed once and cached by the caller. */
+typedef struct geot_plan {
+  int64_t E;              /* edges */
+  int64_t S;              /* dst rows = dst_index[E-1] + 1 (or the caller's dim_size) */
+  int64_t num_segments;   /* non-empty dst rows (index_scatter_cpu.cpp:51 num_nonzero_rows) */
+  int64_t max_degree;     /* longest segment */
+  int32_t is_sorted;      /* 1 iff dst_index is non-decreasing */
+  int32_t has_gaps;       /* 1 iff some row in [0,S) has no edge (num_segments < S) */
+  const int64_t *rowptr;  /* device, S+1 entries: CSR row pointer == geot::coo_to_csr
+                             (geot/match_replace/format_transform.py:5-18); segment r covers edges
+                             [rowptr[r], rowptr[r+1]) */
+} geot_plan_t;
+
+/* Highest index: reads dst_index[E-1] (sorted input) -- one 8-byte D2H copy, synchronises `stream`. */
+GEOT_API int geot_b200_index_last(const int64_t *dst_index, int64_t E, int64_t *last, cudaStream_t stream);
+
+/* Bytes of device memory a plan for (E, S) needs (256-byte aligned buffer). */
+GEOT_API size_t geot_b200_plan_bytes(int64_t E, int64_t S);
+
+/* Builds the plan in plan_buf and fills *plan.  Synchronises `stream` once (to return the
+ * statistics).  dst_index must be sorted for rowptr to be meaningful; is_sorted reports it. */
+GEOT_API int geot_b200_format_preprocess(const int64_t *dst_index, int64_t E, int64_t S, void *plan_buf,
+                                size_t plan_bytes, geot_plan_t *plan, cudaStream_t stream);
+
+/* Edge-balanced contiguous dst-row shards for `parts` GPUs: row_bounds[parts+1]
+ * and edge_bounds[parts+1] (host arrays); shard g owns rows [row_bounds[g], row_bounds[g+1]) and
+ * edges [edge_bounds[g], edge_bounds[g+1]), cut at segment boundaries nearest to g*E/parts.
+ * Synchronises `stream`. */
+GEOT_API int geot_b200_plan_shards(const geot_plan_t *plan, int parts, int64_t *row_bounds,
+                          int64_t *edge_bounds, cudaStream_t stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+
+/* Scratch bytes for one call on E edges with rows of W = H*F elements (256-byte aligned buffer).
+ * sorted == 0 adds the buffers of the edge sort that the unsorted path runs first. */
+GEOT_API size_t geot_b200_workspace_bytes(int64_t E, int64_t W, int dtype, int sorted);
+
+/* Generic entry: all four ops are this call with different operands.
+ *   src        [N_src, H*F]   device, dtype
+ *   src_index  [E] int64 or NULL (NULL: src row = e)
+ *   dst_index  [E] int64, non-decreasing when sorted != 0
+ *   weight     per weight_layout, dtype; NULL iff GEOT_W_NONE
+ *   dst        [S, H*F]       device, dtype; fully overwritten
+ *   plan       optional (NULL allowed): lets the call skip zero-filling when the graph has no
+ *              empty rows; results are identical with and without it. */
+GEOT_API int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                             const void *weight, void *dst, int64_t E, int64_t S, int64_t H,
+                             int64_t F, int dtype, int reduce, int weight_layout, int sorted,
+                             const geot_plan_t *plan, void *workspace, size_t workspace_bytes,
+                             cudaStream_t stream);
+
+/* Replaces index_scatter_cuda (header_cuda.h:4-6; csrc/cuda/index_scatter_cuda.cu:86-105), dim = 0:
+ * src viewed as [E, F] (wrapper/index_scatter_base.h:15-17).  sorted == 0 takes the atomic kernel
+ * (index_scatter_cuda.cu:75-84). */
+GEOT_API int geot_b200_index_scatter(const void *src, const int64_t *index, void *dst, int64_t E, int64_t S,
+                            int64_t F, int dtype, int reduce, int sorted, const geot_plan_t *plan,
+                            void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* Replaces gather_scatter_cuda (header_cuda.h:8-10; csrc/cuda/gather_scatter_cuda.cu:15-28). */
+GEOT_API int geot_b200_gather_scatter(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                             void *dst, int64_t E, int64_t S, int64_t F, int dtype, int reduce,
+                             const geot_plan_t *plan, void *workspace, size_t workspace_bytes,
+                             cudaStream_t stream);
+
+/* Replaces gather_weight_scatter_cuda (header_cuda.h:12-17; gather_weight_scatter_cuda.cu:22-39). */
+GEOT_API int geot_b200_gather_weight_scatter(const void *src, const int64_t *src_index,
+                                    const int64_t *dst_index, const void *weight, void *dst,
+                                    int64_t E, int64_t S, int64_t F, int dtype, int reduce,
+                                    const geot_plan_t *plan, void *workspace,
+                                    size_t workspace_bytes, cudaStream_t stream);
+
+/* Replaces mh_spmm_cuda (header_cuda.h:23-26; csrc/cuda/mh_spmm_cuda.cu:20-38): src [N,H,F],
+ * weight_layout GEOT_W_EDGE_HEAD ([E,H]) or GEOT_W_HEAD_EDGE ([H,E]) (wrapper/mh_spmm_base.h:38-49). */
+GEOT_API int geot_b200_mh_spmm(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                      const void *weight, void *dst, int64_t E, int64_t S, int64_t H, int64_t F,
+                      int dtype, int reduce, int weight_layout, const geot_plan_t *plan,
+                      void *workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* ---- host-buffer entry (end-to-end path) ----------------------------------------------------- */
+
+/* Same operation with every operand in HOST memory (pinned memory makes the copies asynchronous):
+ * stages the operands to the device in edge chunks on two streams so that the copy of chunk i+1
+ * overlaps the reduction of chunk i, reduces, and copies dst back.  Allocates and frees its own
+ * device buffers; returns after dst is complete in host memory.  S must be given.  This is the call
+ * a non-torch host (cgo / JNI / ctypes) makes. */
+GEOT_API int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t *src_index,
+                                  const int64_t *dst_index, const void *weight, void *dst,
+                                  int64_t E, int64_t S, int64_t H, int64_t F, int dtype, int reduce,
+                                  int weight_layout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOT_B200_H_ */

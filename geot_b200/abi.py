@@ -22,7 +22,7 @@ SYMBOLS = [
     "geot_b200_index_last", "geot_b200_plan_bytes", "geot_b200_format_preprocess", "geot_b200_plan_shards",
     "geot_b200_workspace_bytes", "geot_b200_segment_reduce", "geot_b200_index_scatter",
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
-    "geot_b200_segment_reduce_host",
+    "geot_b200_segment_reduce_host", "geot_b200_profile_enable", "geot_b200_profile_read",
 ]
 
 
@@ -63,6 +63,18 @@ def lib() -> ctypes.CDLL:
         L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
         _lib = L
     return _lib
+
+
+def profile_enable(n: int) -> None:
+    check(lib().geot_b200_profile_enable(n), "profile_enable")
+
+
+def profile_read(capacity: int = 4096):
+    """Durations (ms) of the most recent main-kernel launches recorded since profile_enable."""
+    buf = (ctypes.c_float * capacity)()
+    cnt = ctypes.c_int(0)
+    check(lib().geot_b200_profile_read(buf, capacity, ctypes.byref(cnt)), "profile_read")
+    return [buf[i] for i in range(cnt.value)]
 
 
 class AbiError(RuntimeError):

@@ -192,6 +192,14 @@ __global__ void gather_index_kernel(const int64_t *__restrict__ perm, const int6
   if (i < n) out[i] = in[perm[i]];
 }
 
+// ---- instrumentation: event pairs around the main kernel ------------------------------------------
+struct Profile {
+  int n = 0;
+  long long calls = 0;
+  cudaEvent_t *start = nullptr, *stop = nullptr;
+};
+thread_local Profile g_prof;
+
 constexpr int kMaxParts = 64;
 size_t plan_tail_bytes() { return align256(sizeof(PlanStats)) + align256(2 * (kMaxParts + 1) * sizeof(int64_t)); }
 
@@ -378,7 +386,14 @@ int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const in
   p.tail_cnt = w.tail_cnt;
   p.tail_row = w.tail_row;
   p.flags = w.flags;
-  CUDA_TRY(launch(p, cfg.shape, stream));
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_prof.n > 0) {
+    const int slot = (int)(g_prof.calls % g_prof.n);
+    ev0 = g_prof.start[slot];
+    ev1 = g_prof.stop[slot];
+    g_prof.calls += 1;
+  }
+  CUDA_TRY(launch(p, cfg.shape, stream, ev0, ev1));
   return GEOT_OK;
 }
 
@@ -413,6 +428,32 @@ int geot_b200_mh_spmm(const void *src, const int64_t *src_index, const int64_t *
   if (weight_layout != GEOT_W_EDGE_HEAD && weight_layout != GEOT_W_HEAD_EDGE) return GEOT_ERR_INVALID_ARG;
   return geot_b200_segment_reduce(src, src_index, dst_index, weight, dst, E, S, H, F, dtype, reduce, weight_layout, 1,
                                   plan, workspace, workspace_bytes, stream);
+}
+
+int geot_b200_profile_enable(int n) {
+  if (n < 0) return GEOT_ERR_INVALID_ARG;
+  for (int i = 0; i < g_prof.n; ++i) { cudaEventDestroy(g_prof.start[i]); cudaEventDestroy(g_prof.stop[i]); }
+  delete[] g_prof.start; delete[] g_prof.stop;
+  g_prof = Profile();
+  if (n == 0) return GEOT_OK;
+  g_prof.start = new cudaEvent_t[n];
+  g_prof.stop = new cudaEvent_t[n];
+  for (int i = 0; i < n; ++i) { CUDA_TRY(cudaEventCreate(&g_prof.start[i])); CUDA_TRY(cudaEventCreate(&g_prof.stop[i])); }
+  g_prof.n = n;
+  return GEOT_OK;
+}
+
+int geot_b200_profile_read(float *ms, int capacity, int *count) {
+  if (!ms || !count) return GEOT_ERR_INVALID_ARG;
+  const long long have = std::min<long long>(g_prof.calls, g_prof.n);
+  const int k = (int)std::min<long long>(have, capacity);
+  for (int i = 0; i < k; ++i) {
+    const int slot = (int)((g_prof.calls - k + i) % g_prof.n);
+    CUDA_TRY(cudaEventSynchronize(g_prof.stop[slot]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[i], g_prof.start[slot], g_prof.stop[slot]));
+  }
+  *count = k;
+  return GEOT_OK;
 }
 
 // ---- host-buffer entry ------------------------------------------------------------------------------

@@ -53,13 +53,16 @@ cudaError_t launch_shape(const Params &p, const Shape &sh, cudaStream_t stream) 
 #define GEOT_CAT_(a, b, c) a##b##_##c
 #define GEOT_CAT(a, b, c) GEOT_CAT_(a, b, c)
 
-cudaError_t GEOT_CAT(launch_, GEOT_TN, GEOT_RED)(const Params &p, const Shape &sh, cudaStream_t stream) {
+cudaError_t GEOT_CAT(launch_, GEOT_TN, GEOT_RED)(const Params &p, const Shape &sh, cudaStream_t stream,
+                                                  cudaEvent_t ev0, cudaEvent_t ev1) {
   using T = GEOT_T;
   constexpr int FULL = 16 / (int)sizeof(T);
   cudaError_t e;
+  if (ev0) cudaEventRecord(ev0, stream);
   if (sh.vecw == FULL) e = launch_shape<T, FULL, GEOT_RED>(p, sh, stream);
   else if (sh.vecw == 1) e = launch_shape<T, 1, GEOT_RED>(p, sh, stream);
   else return cudaErrorInvalidValue;
+  if (ev1) cudaEventRecord(ev1, stream);
   if (e != cudaSuccess) return e;
   // second pass: segments cut by tile boundaries
   const unsigned blocks = (unsigned)((p.n_tiles + (kThreads / 32) - 1) / (kThreads / 32));

@@ -13,10 +13,11 @@ struct Shape {
   int col_tiles;  // grid.y: ceil(W / (lpr*vpl*vecw))
 };
 
-typedef cudaError_t (*launch_fn)(const Params &, const Shape &, cudaStream_t);
+// ev0 / ev1 (optional): recorded on `stream` right before / after the main kernel (profiling hook)
+typedef cudaError_t (*launch_fn)(const Params &, const Shape &, cudaStream_t, cudaEvent_t, cudaEvent_t);
 
 // defined in inst.cu, one per (dtype, reduce op); index [dtype][red] with red in {sum,max,min,prod}
-#define GEOT_DECL(TN, R) cudaError_t launch_##TN##_##R(const Params &, const Shape &, cudaStream_t);
+#define GEOT_DECL(TN, R) cudaError_t launch_##TN##_##R(const Params &, const Shape &, cudaStream_t, cudaEvent_t, cudaEvent_t);
 GEOT_DECL(f32, 0) GEOT_DECL(f32, 2) GEOT_DECL(f32, 3) GEOT_DECL(f32, 4)
 GEOT_DECL(f64, 0) GEOT_DECL(f64, 2) GEOT_DECL(f64, 3) GEOT_DECL(f64, 4)
 GEOT_DECL(bf16, 0) GEOT_DECL(bf16, 2) GEOT_DECL(bf16, 3) GEOT_DECL(bf16, 4)

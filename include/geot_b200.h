@@ -163,6 +163,16 @@ GEOT_API int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const
                                   int64_t E, int64_t S, int64_t H, int64_t F, int dtype, int reduce,
                                   int weight_layout);
 
+/* ---- instrumentation -------------------------------------------------------------------------- */
+
+/* geot_b200_profile_enable(n > 0): every following segment-reduce call on this host thread records a
+ * CUDA event pair around its MAIN kernel (the fixup pass and any memset stay outside), cycling through
+ * n pairs; n = 0 disables and frees them.  geot_b200_profile_read copies the durations (ms) of the
+ * last min(n, calls) recorded kernels, oldest first, into ms[] and returns their count in *count
+ * (synchronises on the events).  Used by bench.py for the roofline figure; off by default. */
+GEOT_API int geot_b200_profile_enable(int n);
+GEOT_API int geot_b200_profile_read(float *ms, int capacity, int *count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,118 @@
+"""Host-side checks of the drop-in boundary -- no GPU needed, no compute calls.
+
+The C-ABI library must load, export every symbol include/geot_b200.h declares, answer its host-only
+queries, reject bad arguments before touching the device, and the torch bindings must register the
+reference's operator schemas with no CPU implementation behind them (no fallback).
+"""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import geot_b200
+from geot_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "geot_b200.h")).read()
+    return sorted(set(re.findall(r"GEOT_API[^;]*?\b(geot_b200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    assert sorted(abi.SYMBOLS) == declared
+    L = ctypes.CDLL(geot_b200.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_version_arch_status_strings():
+    L = abi.lib()
+    assert L.geot_b200_version() == 100
+    assert L.geot_b200_arch() == 100
+    assert L.geot_b200_status_string(0) == b"ok"
+    assert b"invalid" in L.geot_b200_status_string(1)
+    assert torch.ops.geot.abi_version() == 100
+
+
+def test_library_is_sm100a_only():
+    """The shipped SASS is sm_100a and nothing else (no multi-arch fat binary, no PTX-JIT fallback)."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", geot_b200.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_host_queries():
+    L = abi.lib()
+    assert L.geot_b200_plan_bytes(1000, 10) >= 11 * 8
+    assert L.geot_b200_plan_bytes(1000, 10) % 256 == 0
+    small = L.geot_b200_workspace_bytes(1000, 32, abi.F32, 1)
+    big = L.geot_b200_workspace_bytes(10_000_000, 128, abi.F32, 1)
+    assert 0 < small < big
+    assert small % 256 == 0
+    # the unsorted path needs the sort buffers on top
+    assert L.geot_b200_workspace_bytes(1_000_000, 32, abi.F32, 0) > L.geot_b200_workspace_bytes(1_000_000, 32, abi.F32, 1) + 4 * 8 * 1_000_000 - 4096
+
+
+def test_argument_validation_happens_before_any_device_work():
+    L = abi.lib()
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(256)  # never dereferenced: the calls must fail on validation
+    f = L.geot_b200_segment_reduce
+    assert f(null, null, one, null, one, 10, 4, 1, 8, abi.F32, abi.SUM, abi.W_NONE, 1, None, one, 1 << 20, null) == 1
+    assert f(one, null, one, null, one, 0, 4, 1, 8, abi.F32, abi.SUM, abi.W_NONE, 1, None, one, 1 << 20, null) == 5   # empty
+    assert f(one, null, one, null, one, 10, 4, 1, 8, 9, abi.SUM, abi.W_NONE, 1, None, one, 1 << 20, null) == 1        # dtype
+    assert f(one, null, one, null, one, 10, 4, 1, 8, abi.F32, 7, abi.W_NONE, 1, None, one, 1 << 20, null) == 1        # reduce
+    assert f(one, null, one, null, one, 10, 4, 1, 8, abi.F32, abi.SUM, abi.W_EDGE, 1, None, one, 1 << 20, null) == 1  # weight missing
+    assert f(one, null, one, null, one, 10, 4, 1, 8, abi.F32, abi.SUM, abi.W_NONE, 1, None, ctypes.c_void_p(264), 1 << 20, null) == 3  # misaligned ws
+    assert L.geot_b200_gather_scatter(one, null, one, one, 10, 4, 8, abi.F32, abi.SUM, None, one, 1 << 20, null) == 1  # src_index missing
+    assert L.geot_b200_mh_spmm(one, one, one, one, one, 10, 4, 2, 8, abi.F32, abi.SUM, abi.W_EDGE, None, one, 1 << 20, null) == 1
+    with pytest.raises(abi.AbiError, match="invalid argument"):
+        abi.check(1, "x")
+
+
+def test_operator_schemas_match_the_reference():
+    """csrc/index_scatter.cpp:43-47, gather_scatter.cpp:16-17, gather_weight_scatter.cpp:12-14, mh_spmm.cpp:23."""
+    s = lambda op: str(op.default._schema)
+    assert s(torch.ops.geot.index_scatter) == "geot::index_scatter(int dim, Tensor index, Tensor src, str reduce, bool sorted) -> Tensor"
+    assert s(torch.ops.geot.gather_scatter_impl) == "geot::gather_scatter_impl(Tensor src_index, Tensor dst_index, Tensor src) -> Tensor"
+    assert s(torch.ops.geot.gather_weight_scatter_impl) == "geot::gather_weight_scatter_impl(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src) -> Tensor"
+    assert s(torch.ops.geot.mh_spmm) == "geot::mh_spmm(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src, str reduce) -> Tensor"
+    assert s(torch.ops.geot.gather_scatter) == "geot::gather_scatter(Tensor src_index, Tensor dst_index, Tensor src) -> Tensor"
+    assert s(torch.ops.geot.gather_weight_scatter) == "geot::gather_weight_scatter(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src) -> Tensor"
+
+
+def test_python_surface_matches_the_reference_package():
+    for name in ["index_scatter", "gather_scatter", "gather_weight_scatter", "mh_spmm", "mh_spmm_transposed"]:
+        assert callable(getattr(geot_b200, name))
+    import inspect
+    assert list(inspect.signature(geot_b200.index_scatter).parameters) == ["dim", "src", "index", "reduce", "sorted"]
+    assert list(inspect.signature(geot_b200.mh_spmm).parameters) == ["src_index", "dst_index", "weight", "src", "reduce"]
+
+
+def test_no_cpu_fallback():
+    idx = torch.tensor([0, 0, 1, 2])
+    x = torch.rand(4, 4)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        geot_b200.index_scatter(0, x, idx)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        geot_b200.gather_scatter(idx, idx, x)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        geot_b200.gather_weight_scatter(idx, idx, torch.rand(4), x)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        geot_b200.mh_spmm(idx, idx, torch.rand(4, 2), torch.rand(4, 2, 4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "geot_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "geot_oracle" not in text, f

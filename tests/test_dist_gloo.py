@@ -1,0 +1,95 @@
+"""world_size-2 `gloo` tests of the multi-GPU host logic (geot_b200/dist.py) on CPU.
+
+The reduction kernels need a GPU, so here each rank reduces its shard with the CPU oracle (used as the
+checker of the sharding logic): edge-balanced bounds, local index rebasing, ragged all-gather of src
+rows, and that the concatenated per-rank results equal the unsharded result.
+"""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from geot_b200 import dist as gdist
+    g = torch.Generator().manual_seed(0)          # same graph on every rank
+    N, E, F = 301, 6000, 12
+    deg_w = torch.rand(N, generator=g) ** 3         # skewed in-degrees, some zero-degree rows
+    dst = torch.multinomial(deg_w, E, replacement=True, generator=g).sort().values
+    dst[-1] = N - 1
+    src_index = torch.randint(0, N, (E,), generator=g)
+    weight = torch.rand(E, generator=g)
+    x = torch.rand(N, F, generator=g)
+
+    shard = gdist.shard_graph(src_index, dst, weight, rank, world)
+    rb, eb = shard.row_bounds, shard.edge_bounds
+    assert rb[0] == 0 and rb[-1] == N and eb[0] == 0 and eb[-1] == E
+    assert all(rb[i] <= rb[i + 1] for i in range(world)) and all(eb[i] <= eb[i + 1] for i in range(world))
+    # cuts are at segment boundaries
+    for gg in range(1, world):
+        if 0 < eb[gg] < E:
+            assert dst[eb[gg] - 1] < rb[gg] <= dst[eb[gg]]
+    assert shard.imbalance < 1.2
+
+    # ragged all-gather of the row shards reproduces the replicated matrix
+    x_local = x[rb[rank]:rb[rank + 1]].clone()
+    x_full = gdist.all_gather_rows(x_local, rb)
+    assert torch.equal(x_full, x)
+
+    # each rank reduces its own dst slice (checker = CPU oracle), no reduction collective
+    for reduce in ["sum", "mean", "max"]:
+        if shard.num_local_edges:
+            local = oracle.gather_weight_scatter(shard.src_index, shard.dst_index, shard.weight, x_full, reduce,
+                                                 S=shard.num_local_rows)
+        else:
+            local = torch.zeros(shard.num_local_rows, F)
+        full = oracle.gather_weight_scatter(src_index, dst, weight, x, reduce)
+        assert torch.equal(local, full[rb[rank]:rb[rank + 1]]), reduce
+    dist.barrier()
+    q.put((rank, shard.num_local_edges))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert sum(e for _, e in got) == 6000
+
+
+def test_shard_bounds_rule():
+    from geot_b200 import dist as gdist
+    rowptr = torch.tensor([0, 5, 5, 9, 20, 21, 30])
+    rows, edges = gdist.shard_bounds_from_rowptr(rowptr, 3)
+    assert rows[0] == 0 and rows[-1] == 6 and edges == [int(rowptr[r]) for r in rows]
+    # targets 10 and 20: nearest boundaries are 9 (row 3) and 20 (row 4)
+    assert edges == [0, 9, 20, 30]
+    rows1, edges1 = gdist.shard_bounds_from_rowptr(rowptr, 1)
+    assert rows1 == [0, 6] and edges1 == [0, 30]

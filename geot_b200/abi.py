@@ -38,9 +38,10 @@ _lib = None
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError("geot_b200: %s not built; there is no fallback" % LIB_PATH)
-        L = ctypes.CDLL(LIB_PATH)
+        path = os.environ.get("GEOT_B200_LIB", LIB_PATH)   # tuning builds (Makefile VARIANT=...)
+        if not os.path.exists(path):
+            raise ImportError("geot_b200: %s not built; there is no fallback" % path)
+        L = ctypes.CDLL(path)
         L.geot_b200_status_string.restype = ctypes.c_char_p
         L.geot_b200_last_cuda_error.restype = ctypes.c_char_p
         L.geot_b200_plan_bytes.restype = ctypes.c_size_t

@@ -69,8 +69,8 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok)
   // per-chunk carry handling; shorter ones keep small inputs spread over all 148 SMs.
   int chunk = env_int("GEOT_B200_CHUNK", 0);
   if (chunk <= 0) {
-    chunk = 64;
-    while (chunk > 8 && (E + (int64_t)ng * chunk - 1) / ((int64_t)ng * chunk) < 4 * 148) chunk >>= 1;
+    chunk = 256;
+    while (chunk > 8 && (E + (int64_t)ng * chunk - 1) / ((int64_t)ng * chunk) < 16 * 148) chunk >>= 1;
   }
   c.chunk_edges = chunk;
   c.tile_edges = (int64_t)ng * chunk;
@@ -104,6 +104,9 @@ Workspace carve(void *base, int64_t n_tiles, int64_t W, int dtype) {
 geot::launch_fn pick_launcher(int dtype, int reduce) {
   using namespace geot;
   const int r = (reduce == GEOT_MEAN) ? GEOT_SUM : reduce;
+#ifdef GEOT_MINIMAL   // tuning builds carry the fp32 sum kernels only
+  return (dtype == GEOT_F32 && r == 0) ? launch_f32_0 : nullptr;
+#else
 #define ROW(TN) \
   switch (r) { case 0: return launch_##TN##_0; case 2: return launch_##TN##_2; \
                case 3: return launch_##TN##_3; case 4: return launch_##TN##_4; } break;
@@ -115,6 +118,7 @@ geot::launch_fn pick_launcher(int dtype, int reduce) {
   }
 #undef ROW
   return nullptr;
+#endif
 }
 
 // ---- format_preprocess kernels --------------------------------------------------------------------
@@ -372,11 +376,12 @@ int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const in
   p.E = E;
   p.W = W;
   p.F = F;
-  p.per_head_weight = 0;
   p.ws_e = 1;
   p.ws_h = 0;
-  if (weight_layout == GEOT_W_EDGE_HEAD) { p.ws_e = H; p.ws_h = 1; p.per_head_weight = (H > 1); }
-  if (weight_layout == GEOT_W_HEAD_EDGE) { p.ws_e = 1; p.ws_h = E; p.per_head_weight = (H > 1); }
+  if (weight_layout == GEOT_W_EDGE_HEAD) { p.ws_e = H; p.ws_h = 1; }
+  if (weight_layout == GEOT_W_HEAD_EDGE) { p.ws_e = 1; p.ws_h = E; }
+  geot::Shape shape = cfg.shape;
+  shape.wm = !weight ? geot::WM_NONE : (H == 1 ? geot::WM_EDGE : geot::WM_GENERIC);
   p.mean = (reduce == GEOT_MEAN);
   p.chunk_edges = cfg.chunk_edges;
   p.n_tiles = cfg.n_tiles;
@@ -393,7 +398,7 @@ int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const in
     ev1 = g_prof.stop[slot];
     g_prof.calls += 1;
   }
-  CUDA_TRY(launch(p, cfg.shape, stream, ev0, ev1));
+  CUDA_TRY(launch(p, shape, stream, ev0, ev1));
   return GEOT_OK;
 }
 

@@ -187,6 +187,7 @@ at::Tensor index_scatter_cuda_impl(int64_t dim, at::Tensor index, at::Tensor src
   TORCH_CHECK(index.dim() == 1, "index must be 1 dimensional");
   TORCH_CHECK(src.size(dim) == index.size(0), "index length must be equal to src dimension size");
   const int red = reduce_enum(reduce);
+  TORCH_CHECK(index.size(0) > 0, "geot::index_scatter: index is empty (the output size is index[-1] + 1)");
   at::Tensor s = (dim == 0) ? src : src.movedim(dim, 0);
   s = s.contiguous();
   const int64_t E = index.size(0);

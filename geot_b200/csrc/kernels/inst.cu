@@ -10,13 +10,13 @@
 namespace geot {
 namespace {
 
-template <typename T, int VECW, int LPR, int VPL, int RED>
-cudaError_t launch_one(const Params &p, const Shape &sh, cudaStream_t stream) {
+template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
+cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
   using A = typename AccOf<T>::type;
   constexpr int NG = kThreads / LPR;
   constexpr int CW = LPR * VPL * VECW;
   constexpr size_t smem = 2 * (size_t)NG * CW * sizeof(A) + (size_t)NG * (4 * 8 + 4);
-  auto kern = segment_reduce_kernel<T, VECW, LPR, VPL, RED>;
+  auto kern = segment_reduce_kernel<T, VECW, LPR, VPL, RED, WM>;
   if (smem > 48 * 1024) {
     static bool configured = false;   // per instantiation
     if (!configured) {
@@ -25,9 +25,20 @@ cudaError_t launch_one(const Params &p, const Shape &sh, cudaStream_t stream) {
       configured = true;
     }
   }
-  dim3 grid((unsigned)p.n_tiles, (unsigned)sh.col_tiles);
-  kern<<<grid, kThreads, smem, stream>>>(p);
+  const long long blocks = (long long)p.n_tiles * sh.col_tiles;
+  if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)blocks, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+// sum kernels exist per weight mode; max / min / prod are built for the generic weight mode only
+template <typename T, int VECW, int LPR, int VPL, int RED>
+cudaError_t launch_one(const Params &p, const Shape &sh, cudaStream_t stream) {
+  if constexpr (RED == RED_SUM) {
+    if (sh.wm == WM_NONE) return launch_wm<T, VECW, LPR, VPL, RED, WM_NONE>(p, sh, stream);
+    if (sh.wm == WM_EDGE) return launch_wm<T, VECW, LPR, VPL, RED, WM_EDGE>(p, sh, stream);
+  }
+  return launch_wm<T, VECW, LPR, VPL, RED, WM_GENERIC>(p, sh, stream);
 }
 
 template <typename T, int VECW, int RED>

@@ -10,7 +10,8 @@ struct Shape {
   int vecw;       // elements per lane vector (16 bytes worth, or 1 for the unaligned fallback)
   int lpr;        // lanes per row (group size): power of two <= 32
   int vpl;        // vectors per lane: 1, 2 or 4 (only with lpr == 32)
-  int col_tiles;  // grid.y: ceil(W / (lpr*vpl*vecw))
+  int col_tiles;  // ceil(W / (lpr*vpl*vecw)); grid.x = n_tiles * col_tiles, column tile is the slow index
+  int wm;         // WM_NONE / WM_EDGE / WM_GENERIC (sum kernels; the other reduce ops are built WM_GENERIC only)
 };
 
 // ev0 / ev1 (optional): recorded on `stream` right before / after the main kernel (profiling hook)

@@ -10,17 +10,21 @@
 //     consecutive chunks.  Every CTA does the same number of edges whatever the degree skew.
 //   * A group keeps the whole feature row in registers: lane gl holds VPL vectors of VECW elements
 //     (128-bit loads when the row allows it), so one row = one coalesced 16*LPR-byte request.
-//   * Segment detection from the sorted index: each lane loads one dst index of the batch, compares
-//     it with its left neighbour (shfl_up) and a ballot gives the group a bitmask of segment heads;
-//     a batch with no head runs the branch-free accumulate loop.
+//   * Index / weight streams are read once per edge, coalesced (lane l of the group loads edge l of
+//     the batch and turns its src index into a row byte offset); offset, weight and the segment-head
+//     flags reach the other lanes by shuffle / ballot.  These read-once streams carry an L2
+//     evict-first policy so that they do not push the re-used src rows out of L2.
+//   * Segment detection from the sorted index: each lane compares its dst index with its left
+//     neighbour (shfl_up); the ballot is the batch's bitmask of segment heads.  A run of edges
+//     without a head takes a branch-free accumulate loop.
 //   * No atomics and no pre-zeroed dst.  A segment that lies inside a chunk is stored once with a
-//     plain vector store.  A segment cut by a chunk boundary leaves a partial ("carry") in shared
-//     memory; after one __syncthreads the owner of the segment's first partial adds the later ones
-//     in order.  Only segments cut by a TILE boundary leave the CTA: their partials go to the
-//     workspace and segment_fixup_kernel finishes them (one chain per cut segment).  The summation
-//     tree is fixed by (E, chunk_edges) alone, so results are bit-reproducible run to run.
-//   * U independent row loads are issued before the first is consumed (memory-level parallelism
-//     for the L2-resident gather); index / weight streams are read once per edge, coalesced.
+//     plain vector store.  A segment cut by a chunk boundary leaves a partial in shared memory;
+//     after one __syncthreads the owner of the segment's first partial adds the later ones in
+//     order.  Only segments cut by a TILE boundary leave the CTA: their partials go to the workspace
+//     and segment_fixup_kernel finishes them.  The summation tree depends on (E, chunk_edges)
+//     alone, so results are bit-reproducible run to run.
+//   * U independent row loads are issued before the first is consumed, and the next batch's
+//     index / weight loads are issued before the current batch is processed.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -31,6 +35,9 @@ namespace geot {
 
 enum : int { RED_SUM = 0, RED_MEAN = 1, RED_MAX = 2, RED_MIN = 3, RED_PROD = 4 };
 enum : int { FLAG_HEAD = 1, FLAG_THROUGH = 2, FLAG_TAIL = 4 };
+// weight handling inside the kernel: none / one weight per edge (shuffled) / generic (per-lane loads:
+// the per-head weights of mh_spmm; also serves the rarely used reduce ops for every weight layout)
+enum : int { WM_NONE = 0, WM_EDGE = 1, WM_GENERIC = 2 };
 
 constexpr int kThreads = 256;
 
@@ -44,7 +51,6 @@ struct Params {
   int64_t W;                 // row width in elements (H*F)
   int64_t F;                 // per-head width
   int64_t ws_e, ws_h;        // weight element (e,h) at weight[e*ws_e + h*ws_h]
-  int per_head_weight;       // 1: weight differs per head (mh_spmm); 0: one weight per edge
   int mean;                  // 1: divide by the segment length at the end
   int chunk_edges;           // edges per group chunk
   int64_t n_tiles;
@@ -92,16 +98,47 @@ template <int LPR> __device__ __forceinline__ unsigned group_mask(int lane) {
     return ((1u << LPR) - 1u) << (lane & ~(LPR - 1));
   }
 }
+template <int N> __device__ __forceinline__ unsigned low_bits() {
+  if constexpr (N >= 32) return 0xffffffffu;
+  else return (1u << N) - 1u;
+}
+
+// Read-once streams (indices, per-edge weights): bypass L1, first in line for L2 eviction.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int64_t ld_stream(const int64_t *p, uint64_t pol) {
+  int64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <typename T> __device__ __forceinline__ T ld_stream_t(const T *p, uint64_t) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld_stream_t<float>(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
 
 // ---- main kernel -------------------------------------------------------------------------------
-template <typename T, int VECW, int LPR, int VPL, int RED>
-__global__ void __launch_bounds__(kThreads)
+// tuning knobs (compile time): row loads in flight per group, minimum resident CTAs per SM
+#ifndef GEOT_U0
+#define GEOT_U0 8
+#endif
+#ifndef GEOT_MINB
+#define GEOT_MINB 2
+#endif
+
+template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
+__global__ void __launch_bounds__(kThreads, (VPL == 1 ? GEOT_MINB : (VPL == 2 ? 2 : 1)))
 segment_reduce_kernel(const Params p) {
   using A = typename AccOf<T>::type;
   using VecT = Vec<T, VECW>;
   constexpr int NG = kThreads / LPR;      // chunks per tile
-  constexpr int CW = LPR * VPL * VECW;    // columns per CTA (grid.y tiles wider rows)
-  constexpr int U = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);  // row loads in flight per group
+  constexpr int CW = LPR * VPL * VECW;    // columns per CTA
+  constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0);
+  constexpr int U = (LPR < U0) ? LPR : U0;   // row loads in flight per group
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A *s_head = reinterpret_cast<A *>(smem_raw);              // [NG][CW]
@@ -119,8 +156,12 @@ segment_reduce_kernel(const Params p) {
   const unsigned gmask = group_mask<LPR>(lane);
   const int gshift = lane & ~(LPR - 1);
 
-  const int64_t tile = blockIdx.x;
-  const int64_t col0 = (int64_t)blockIdx.y * CW;
+  // Column tiles are the slow index of the grid: every tile of column tile 0 is scheduled before
+  // column tile 1, so a wide row is swept in column slabs.
+  const int64_t tile = (int64_t)blockIdx.x % p.n_tiles;
+  const int64_t col_tile = (int64_t)blockIdx.x / p.n_tiles;
+  const int64_t col0 = col_tile * CW;
+  const bool first_col_tile = (col_tile == 0);
   const int64_t E = p.E, W = p.W;
   const int C = p.chunk_edges;
   const int64_t e_begin = (tile * NG + g) * (int64_t)C;
@@ -131,24 +172,31 @@ segment_reduce_kernel(const Params p) {
   const int64_t *__restrict__ dst_index = p.dst_index;
   const int64_t *__restrict__ src_index = p.src_index;
   T *__restrict__ dst = static_cast<T *>(p.dst);
+  const uint64_t pol = policy_evict_first();
 
-  // this lane's columns and (mh_spmm) the weight offset of the head each vector belongs to
+  // This lane's columns.  Lanes past the row end re-read a valid column (same sectors as another
+  // lane, no extra traffic) and never store: the hot loop carries no column predicate.
   int64_t col[VPL];
   bool col_ok[VPL];
-  int64_t hoff[VPL];
+  const char *lane_src[VPL];    // src + clamped column, as bytes
+  const T *lane_w[VPL];         // WM_GENERIC: weight + head offset of this vector (null: no weight)
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     col[j] = col0 + (int64_t)(j * LPR + gl) * VECW;
     col_ok[j] = col[j] < W;
-    hoff[j] = (p.per_head_weight && col_ok[j]) ? (col[j] / p.F) * p.ws_h : 0;
+    const int64_t c = col_ok[j] ? col[j] : col0;
+    lane_src[j] = reinterpret_cast<const char *>(src + c);
+    lane_w[j] = (WM == WM_GENERIC && weight != nullptr) ? weight + (c / p.F) * p.ws_h : nullptr;
   }
+  const int64_t row_bytes = W * (int64_t)sizeof(T);
 
-  A acc[VPL][VECW];
+  A acc[VPL][VECW];    // the open run
+  A hacc[VPL][VECW];   // the chunk's HEAD partial, once closed
 #pragma unroll
   for (int j = 0; j < VPL; ++j)
 #pragma unroll
-    for (int i = 0; i < VECW; ++i) acc[j][i] = red_identity<RED, A>();
-  long long cnt = 0;
+    for (int i = 0; i < VECW; ++i) { acc[j][i] = red_identity<RED, A>(); hacc[j][i] = red_identity<RED, A>(); }
+  long long cnt = 0, hcnt = 0;
   int flags = 0;
 
   auto finalize_store = [&](int64_t row, A(&a)[VPL][VECW], long long n) {
@@ -169,98 +217,153 @@ segment_reduce_kernel(const Params p) {
   if (e_begin < e_end) {
     const int64_t prev_row = (e_begin > 0) ? dst_index[e_begin - 1] : -1;
     const int64_t next_row = (e_end < E) ? dst_index[e_end] : -1;
-    int64_t cur_row = dst_index[e_begin];
-    int64_t last_dst = cur_row;          // dst of the edge left of the current batch
-    bool is_head = (cur_row == prev_row);
+    int64_t last_dst = dst_index[e_begin];   // dst of the edge left of the current batch
+    bool is_head = (last_dst == prev_row);   // the open run entered the chunk from the left
 
-    // ends the current run: a complete segment is stored, a cut one is parked in shared memory
-    auto flush = [&](bool continues) {
+    // closes the open run, whose row is `row`
+    auto close_run = [&](int64_t row) {
       if (is_head) {
 #pragma unroll
         for (int j = 0; j < VPL; ++j)
 #pragma unroll
-          for (int i = 0; i < VECW; ++i) s_head[g * CW + (j * LPR + gl) * VECW + i] = acc[j][i];
-        if (gl == 0) { s_head_cnt[g] = cnt; s_head_row[g] = cur_row; }
-        flags |= FLAG_HEAD | (continues ? FLAG_THROUGH : 0);
-      } else if (continues) {
-#pragma unroll
-        for (int j = 0; j < VPL; ++j)
-#pragma unroll
-          for (int i = 0; i < VECW; ++i) s_tail[g * CW + (j * LPR + gl) * VECW + i] = acc[j][i];
-        if (gl == 0) { s_tail_cnt[g] = cnt; s_tail_row[g] = cur_row; }
-        flags |= FLAG_TAIL;
+          for (int i = 0; i < VECW; ++i) hacc[j][i] = acc[j][i];
+        hcnt = cnt;
+        flags |= FLAG_HEAD;
+        is_head = false;
       } else {
-        finalize_store(cur_row, acc, cnt);
+        finalize_store(row, acc, cnt);
       }
 #pragma unroll
       for (int j = 0; j < VPL; ++j)
 #pragma unroll
         for (int i = 0; i < VECW; ++i) acc[j][i] = red_identity<RED, A>();
       cnt = 0;
-      is_head = false;
     };
+
+    auto accumulate = [&](const VecT(&v)[VPL], const A(&w)[VPL]) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+#pragma unroll
+        for (int i = 0; i < VECW; ++i) {
+          A x = to_acc<T>(v[j].v[i]);
+          if (WM != WM_NONE) x = x * w[j];
+          acc[j][i] = red_op<RED, A>(acc[j][i], x);
+        }
+    };
+
+    // batch operands of this lane: edge (b + gl)
+    auto load_batch = [&](int64_t b, int nb, int64_t &my_dst, int64_t &my_off, A &my_w) {
+      const int64_t my_e = b + gl;
+      const bool valid = gl < nb;
+      my_dst = valid ? ld_stream(dst_index + my_e, pol) : (int64_t)-2;
+      const int64_t s = valid ? (src_index ? ld_stream(src_index + my_e, pol) : my_e) : 0;
+      my_off = s * row_bytes;
+      my_w = A(1);
+      if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + my_e, pol));
+    };
+
+    int64_t my_dst, my_off;
+    A my_w;
+    load_batch(e_begin, (int)min((int64_t)LPR, e_end - e_begin), my_dst, my_off, my_w);
 
     for (int64_t b = e_begin; b < e_end; b += LPR) {
       const int nb = (int)min((int64_t)LPR, e_end - b);
-      const int64_t my_e = b + gl;
-      const bool valid = gl < nb;
-      const int64_t my_dst = valid ? dst_index[my_e] : last_dst;
-      const int64_t my_src = valid ? (src_index ? src_index[my_e] : my_e) : 0;
-      A my_w = A(1);
-      if (weight != nullptr && !p.per_head_weight && valid) my_w = to_acc<T>(weight[my_e * p.ws_e]);
+      // issue the next batch's operand loads before touching this batch
+      int64_t n_dst = -2, n_off = 0;
+      A n_w = A(1);
+      if (b + LPR < e_end) load_batch(b + LPR, (int)min((int64_t)LPR, e_end - b - LPR), n_dst, n_off, n_w);
 
       // segment heads of this batch as a bitmask (bit k: edge b+k starts a new dst row)
       int64_t left = __shfl_up_sync(gmask, my_dst, 1, LPR);
       if (gl == 0) left = last_dst;
-      const unsigned bmask = (__ballot_sync(gmask, valid && my_dst != left) >> gshift);
+      const unsigned bmask = (__ballot_sync(gmask, gl < nb && my_dst != left) >> gshift) & low_bits<LPR>();
+      const int64_t batch_left = last_dst;
       last_dst = __shfl_sync(gmask, my_dst, nb - 1, LPR);
 
-      for (int k0 = 0; k0 < nb; k0 += U) {
-        VecT v[U][VPL];
-        A w[U][VPL];
-        // ---- issue U row loads --------------------------------------------------------------
+      if (nb == LPR) {
+        // ---- full batch: U loads in flight, branch-free when the U edges hold no segment head ----
+#pragma unroll 1
+        for (int k0 = 0; k0 < LPR; k0 += U) {
+          VecT v[U][VPL];
+          A w[U][VPL];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int k = k0 + u;
-          const int ks = (k < nb) ? k : (nb - 1);   // keep shuffles convergent; result unused if k>=nb
-          const int64_t s = __shfl_sync(gmask, my_src, ks, LPR);
-          const A we = __shfl_sync(gmask, my_w, ks, LPR);
-          if (k < nb) {
-            const T *rowp = src + s * W;
+          for (int u = 0; u < U; ++u) {
+            const int64_t off = __shfl_sync(gmask, my_off, k0 + u, LPR);
+            const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
 #pragma unroll
             for (int j = 0; j < VPL; ++j) {
-              if (col_ok[j]) v[u][j] = *reinterpret_cast<const VecT *>(rowp + col[j]);
+              v[u][j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
               w[u][j] = we;
-              if (p.per_head_weight && col_ok[j])
-                w[u][j] = to_acc<T>(weight[(b + k) * p.ws_e + hoff[j]]);
+              if (WM == WM_GENERIC && lane_w[j] != nullptr) w[u][j] = to_acc<T>(__ldg(lane_w[j] + (b + k0 + u) * p.ws_e));
+            }
+          }
+          const unsigned sub = (bmask >> k0) & low_bits<U>();
+          if (sub == 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) accumulate(v[u], w[u]);
+            cnt += U;
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if ((sub >> u) & 1u) {
+                const int k = k0 + u;
+                const int64_t row = (k == 0) ? batch_left : __shfl_sync(gmask, my_dst, (k == 0) ? 0 : k - 1, LPR);
+                close_run(row);
+              }
+              accumulate(v[u], w[u]);
+              ++cnt;
             }
           }
         }
-        // ---- consume in edge order ------------------------------------------------------------
+      } else {
+        // ---- ragged last batch of the edge list: one edge at a time ---------------------------------
+        for (int k = 0; k < nb; ++k) {
+          const int64_t off = __shfl_sync(gmask, my_off, k, LPR);
+          const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k, LPR) : A(1);
+          const int64_t row = __shfl_sync(gmask, my_dst, k > 0 ? k - 1 : 0, LPR);
+          VecT v[VPL];
+          A w[VPL];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int k = k0 + u;
-          if (k < nb) {
-            if ((bmask >> k) & 1u) {
-              flush(false);
-              cur_row = __shfl_sync(gmask, my_dst, k, LPR);
-            }
-#pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-              if (!col_ok[j]) continue;
-#pragma unroll
-              for (int i = 0; i < VECW; ++i) {
-                A x = to_acc<T>(v[u][j].v[i]);
-                if (weight != nullptr) x = x * w[u][j];
-                acc[j][i] = red_op<RED, A>(acc[j][i], x);
-              }
-            }
-            ++cnt;
+          for (int j = 0; j < VPL; ++j) {
+            v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
+            w[j] = we;
+            if (WM == WM_GENERIC && lane_w[j] != nullptr) w[j] = to_acc<T>(__ldg(lane_w[j] + (b + k) * p.ws_e));
           }
+          if ((bmask >> k) & 1u) close_run(k == 0 ? batch_left : row);
+          accumulate(v, w);
+          ++cnt;
         }
       }
+      my_dst = n_dst; my_off = n_off; my_w = n_w;
     }
-    flush(cur_row == next_row);
+
+    // the run still open at the chunk end
+    const int64_t cur_row = last_dst;
+    const bool continues = (cur_row == next_row);
+    if (is_head) {                      // the whole chunk is one run that entered from the left
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+#pragma unroll
+        for (int i = 0; i < VECW; ++i) hacc[j][i] = acc[j][i];
+      hcnt = cnt;
+      flags |= FLAG_HEAD | (continues ? FLAG_THROUGH : 0);
+    } else if (continues) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+#pragma unroll
+        for (int i = 0; i < VECW; ++i) s_tail[g * CW + (j * LPR + gl) * VECW + i] = acc[j][i];
+      if (gl == 0) { s_tail_cnt[g] = cnt; s_tail_row[g] = cur_row; }
+      flags |= FLAG_TAIL;
+    } else {
+      finalize_store(cur_row, acc, cnt);
+    }
+    if (flags & FLAG_HEAD) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+#pragma unroll
+        for (int i = 0; i < VECW; ++i) s_head[g * CW + (j * LPR + gl) * VECW + i] = hacc[j][i];
+      if (gl == 0) { s_head_cnt[g] = hcnt; s_head_row[g] = prev_row; }
+    }
   }
   if (gl == 0) s_flags[g] = flags;
   __syncthreads();
@@ -298,7 +401,7 @@ segment_reduce_kernel(const Params p) {
 #pragma unroll
       for (int i = 0; i < VECW; ++i) out[col[j] + i] = a[j][i];
     }
-    if (gl == 0 && blockIdx.y == 0) {
+    if (gl == 0 && first_col_tile) {
       if (from_tile_head) p.head_cnt[tile] = n;
       else { p.tail_cnt[tile] = n; p.tail_row[tile] = row; }
     }
@@ -312,7 +415,7 @@ segment_reduce_kernel(const Params p) {
   if (flags & FLAG_TAIL) run_chain(s_tail + g * CW, s_tail_cnt[g], s_tail_row[g], g + 1, false);
 
   // tile-level flags follow from the index alone
-  if (tid == 0 && blockIdx.y == 0) {
+  if (tid == 0 && first_col_tile) {
     const int64_t t_begin = tile * NG * (int64_t)C;
     const int64_t t_end = min(t_begin + (int64_t)NG * C, E);
     const int64_t first_row = dst_index[t_begin], last_row = dst_index[t_end - 1];
@@ -325,30 +428,89 @@ segment_reduce_kernel(const Params p) {
 }
 
 // ---- fixup: finish the segments cut by tile boundaries -------------------------------------------
-// One warp per tile whose last segment continues into the next tile: tail[t] + head[t+1] + ... up to
-// and including the first head that is not THROUGH.  Lanes stride over the W columns.
+// A chain = tail[t] + head[t+1] + ... up to and including the first head that is not THROUGH.
+// A CTA looks at 8 consecutive tiles.  Short chains: one warp each, lanes across the columns, the
+// chain loop unrolled so that its loads overlap.  Long chains (a hub row cut by hundreds of tiles):
+// all 8 warps stride over the chain, then the 8 partials are combined in warp order -- still a fixed
+// summation order.
 template <typename T, int RED>
 __global__ void __launch_bounds__(kThreads)
 segment_fixup_kernel(const Params p) {
   using A = typename AccOf<T>::type;
-  const int64_t t = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (t >= p.n_tiles) return;
-  if (!(p.flags[t] & FLAG_TAIL)) return;
+  constexpr int NW = kThreads / 32;
+  constexpr int kLong = 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t W = p.W;
-  const A *tail = static_cast<const A *>(p.carry_tail) + t * W;
   const A *head = static_cast<const A *>(p.carry_head);
-  T *dst = static_cast<T *>(p.dst) + p.tail_row[t] * W;
-  // chain length first (flags are bytes: cheap), then the sums column by column
+  __shared__ int64_t s_last[NW];
+  __shared__ int s_is_long[NW];
+  __shared__ A s_part[NW * 32];
+
+  const int64_t t = (int64_t)blockIdx.x * NW + warp;
+  const bool has = (t < p.n_tiles) && (p.flags[t] & FLAG_TAIL);
   int64_t last = t + 1;
-  while (p.flags[last] & FLAG_THROUGH) ++last;
-  long long n = p.tail_cnt[t];
-  for (int64_t j = t + 1; j <= last; ++j) n += p.head_cnt[j];
-  for (int64_t c = lane; c < W; c += 32) {
-    A a = tail[c];
-    for (int64_t j = t + 1; j <= last; ++j) a = red_op<RED, A>(a, head[j * W + c]);
-    if (p.mean) a = a / static_cast<A>(n);
-    dst[c] = from_acc<T>(a);
+  if (has) {
+    // chain end: scan the THROUGH flags 32 tiles at a time
+    for (;;) {
+      const int64_t q = last + lane;
+      const bool thr = (q < p.n_tiles) && (p.flags[q] & FLAG_THROUGH);
+      const unsigned m = __ballot_sync(0xffffffffu, !thr);
+      if (m) { last += __ffs(m) - 1; break; }
+      last += 32;
+    }
+  }
+  const bool is_long = has && (last - t > kLong);
+  if (lane == 0) { s_last[warp] = last; s_is_long[warp] = is_long ? 1 : 0; }
+
+  if (has && !is_long) {
+    long long n = p.tail_cnt[t];
+    for (int64_t j = t + 1; j <= last; ++j) n += p.head_cnt[j];
+    const A *tail = static_cast<const A *>(p.carry_tail) + t * W;
+    T *dst = static_cast<T *>(p.dst) + p.tail_row[t] * W;
+    for (int64_t c = lane; c < W; c += 32) {
+      A a = tail[c];
+      int64_t j = t + 1;
+      for (; j + 3 <= last; j += 4) {
+        const A x0 = head[j * W + c], x1 = head[(j + 1) * W + c], x2 = head[(j + 2) * W + c], x3 = head[(j + 3) * W + c];
+        a = red_op<RED, A>(red_op<RED, A>(red_op<RED, A>(red_op<RED, A>(a, x0), x1), x2), x3);
+      }
+      for (; j <= last; ++j) a = red_op<RED, A>(a, head[j * W + c]);
+      if (p.mean) a = a / static_cast<A>(n);
+      dst[c] = from_acc<T>(a);
+    }
+  }
+  __syncthreads();
+  // long chains, one after the other, by the whole CTA
+  for (int wv = 0; wv < NW; ++wv) {
+    if (!s_is_long[wv]) continue;          // uniform across the CTA
+    const int64_t tt = (int64_t)blockIdx.x * NW + wv;
+    const int64_t lst = s_last[wv];
+    long long n = 0;
+    for (int64_t j = tt + 1 + lane; j <= lst; j += 32) n += p.head_cnt[j];
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    n += p.tail_cnt[tt];
+    for (int64_t c0 = 0; c0 < W; c0 += 32) {
+      const int64_t c = c0 + lane;
+      A a = red_identity<RED, A>();
+      if (c < W) {
+        int64_t j = tt + 1 + warp;
+        for (; j + 3 * NW <= lst; j += 4 * NW) {
+          const A x0 = head[j * W + c], x1 = head[(j + NW) * W + c], x2 = head[(j + 2 * NW) * W + c], x3 = head[(j + 3 * NW) * W + c];
+          a = red_op<RED, A>(red_op<RED, A>(red_op<RED, A>(red_op<RED, A>(a, x0), x1), x2), x3);
+        }
+        for (; j <= lst; j += NW) a = red_op<RED, A>(a, head[j * W + c]);
+      }
+      s_part[warp * 32 + lane] = a;
+      __syncthreads();
+      if (warp == 0 && c < W) {
+        A r = static_cast<const A *>(p.carry_tail)[tt * W + c];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) r = red_op<RED, A>(r, s_part[k * 32 + lane]);
+        if (p.mean) r = r / static_cast<A>(n);
+        (static_cast<T *>(p.dst) + p.tail_row[tt] * W)[c] = from_acc<T>(r);
+      }
+      __syncthreads();
+    }
   }
 }
 

@@ -91,7 +91,7 @@ def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H
     dst_index = dst_index.contiguous().cpu()
     E = dst_index.numel()
     if S is None:
-        S = int(dst_index[-1]) + 1
+        S = int(dst_index.max()) + 1      # == dst_index[-1] + 1 for sorted input
     shp = list(src.shape)
     N = shp[0]
     W = int(np.prod(shp[1:])) if len(shp) > 1 else 1

@@ -1,0 +1,31 @@
+"""Times one workload through the C ABI for the library named by GEOT_B200_LIB over chunk sizes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from geot_b200 import abi
+
+name = sys.argv[1] if len(sys.argv) > 1 else "reddit_gws"
+chunks = [int(c) for c in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["0"])]
+wk = bench.build_workload(name, "cuda")
+E, S, F, H = wk["E"], wk["S"], wk["F"], wk["H"]
+w = wk["w"]
+layout = abi.W_NONE if w is None else (abi.W_EDGE if w.dim() == 1 else abi.W_EDGE_HEAD)
+plan = abi.DevicePlan(wk["di"], S)
+out = torch.empty([S] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device="cuda")
+for c in chunks:
+    os.environ["GEOT_B200_CHUNK"] = str(c)
+    ws = abi.Workspace(E, F * H, wk["dtype"], "cuda")
+    f = lambda: abi.segment_reduce(wk["x"], wk["si"], wk["di"], w, "sum", S=S, H=H, weight_layout=layout, plan=plan, out=out, workspace=ws)
+    for _ in range(3): f()
+    abi.profile_enable(10)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): f()
+    e1.record(); torch.cuda.synchronize()
+    km = abi.profile_read(10); abi.profile_enable(0)
+    ms = e0.elapsed_time(e1) / 10
+    print("%s lib=%s chunk=%d: step %.3f ms (%.0f GB/s logical, %.2f Gedge/s)  main kernel %.3f ms  fixup+gaps %.3f ms" % (
+        name, os.path.basename(os.environ.get("GEOT_B200_LIB", "default")), c, ms, wk["bytes_logical"] / ms / 1e6, E / ms / 1e6,
+        sum(km) / len(km), ms - sum(km) / len(km)), flush=True)

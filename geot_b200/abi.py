@@ -22,7 +22,7 @@ SYMBOLS = [
     "geot_b200_index_last", "geot_b200_plan_bytes", "geot_b200_format_preprocess", "geot_b200_plan_shards",
     "geot_b200_workspace_bytes", "geot_b200_segment_reduce", "geot_b200_index_scatter",
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
-    "geot_b200_segment_reduce_host", "geot_b200_profile_enable", "geot_b200_profile_read",
+    "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
 ]
 
 

@@ -57,8 +57,11 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok)
     lpr = pow2ceil(nvec);
     vpl = 1;
   } else {
+    // wider rows: several vectors per lane, capped so that the accumulators stay within 16 registers
+    // (fp32: 4 vectors, fp64: 4, bf16/fp16 with 8-element vectors: 2); beyond that, column tiles
+    const int vpl_max = (vecw == 8) ? 2 : 4;
     lpr = 32;
-    vpl = nvec <= 64 ? 2 : 4;
+    vpl = (nvec <= 64 || vpl_max == 2) ? 2 : 4;
   }
   c.shape.vecw = vecw;
   c.shape.lpr = lpr;
@@ -304,10 +307,14 @@ size_t geot_b200_workspace_bytes(int64_t E, int64_t W, int dtype, int sorted) {
   return best + 4 * align256((size_t)E * 8) + align256(cub_bytes);
 }
 
-int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const int64_t *dst_index,
-                             const void *weight, void *dst, int64_t E, int64_t S, int64_t H, int64_t F,
-                             int dtype, int reduce, int weight_layout, int sorted, const geot_plan_t *plan,
-                             void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+}  // extern "C"
+
+namespace {
+// clear_mode: 0 = decide from the plan (public behaviour), 1 = never clear (the caller cleared dst itself)
+int segment_reduce_impl(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                        const void *weight, void *dst, int64_t E, int64_t S, int64_t H, int64_t F,
+                        int dtype, int reduce, int weight_layout, int sorted, const geot_plan_t *plan,
+                        void *workspace, size_t workspace_bytes, cudaStream_t stream, int clear_mode) {
   if (!src || !dst_index || !dst) return GEOT_ERR_INVALID_ARG;
   if (E <= 0) return GEOT_ERR_EMPTY;
   if (S <= 0 || H <= 0 || F <= 0) return GEOT_ERR_INVALID_ARG;
@@ -364,7 +371,7 @@ int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const in
 
   // Rows that receive no edge must read 0.  The kernels store every non-empty row exactly once and
   // never touch the others, so dst is cleared first unless the plan proves there is no empty row.
-  const bool need_clear = !(plan && !plan->has_gaps && plan->S == S);
+  const bool need_clear = clear_mode == 0 && !(plan && !plan->has_gaps && plan->S == S);
   if (need_clear) CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)S * (size_t)W * dtype_size(dtype), stream));
 
   geot::Params p;
@@ -400,6 +407,17 @@ int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const in
   }
   CUDA_TRY(launch(p, shape, stream, ev0, ev1));
   return GEOT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                             const void *weight, void *dst, int64_t E, int64_t S, int64_t H, int64_t F,
+                             int dtype, int reduce, int weight_layout, int sorted, const geot_plan_t *plan,
+                             void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return segment_reduce_impl(src, src_index, dst_index, weight, dst, E, S, H, F, dtype, reduce, weight_layout, sorted,
+                             plan, workspace, workspace_bytes, stream, 0);
 }
 
 int geot_b200_index_scatter(const void *src, const int64_t *index, void *dst, int64_t E, int64_t S, int64_t F,
@@ -462,6 +480,37 @@ int geot_b200_profile_read(float *ms, int capacity, int *count) {
 }
 
 // ---- host-buffer entry ------------------------------------------------------------------------------
+// Pipeline: src first, then the sorted edge list in slices cut at segment boundaries.  Slice k+1 is
+// copied (H2D stream) while slice k is reduced (compute stream) and the finished dst rows of slice k-1
+// travel back (D2H stream, the other direction of the link).  Device buffers live in a per-process
+// arena that grows on demand and is reused across calls.
+namespace {
+struct Arena {
+  char *base = nullptr;
+  size_t bytes = 0;
+  cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+  static constexpr int kMaxSlices = 64;
+  cudaEvent_t copied[kMaxSlices] = {}, reduced[kMaxSlices] = {};
+  cudaEvent_t src_ready = nullptr;
+};
+Arena g_arena;
+}  // namespace
+
+int geot_b200_host_arena_release(void) {
+  Arena &a = g_arena;
+  if (a.base) cudaFree(a.base);
+  for (int i = 0; i < Arena::kMaxSlices; ++i) {
+    if (a.copied[i]) cudaEventDestroy(a.copied[i]);
+    if (a.reduced[i]) cudaEventDestroy(a.reduced[i]);
+  }
+  if (a.src_ready) cudaEventDestroy(a.src_ready);
+  if (a.h2d) cudaStreamDestroy(a.h2d);
+  if (a.comp) cudaStreamDestroy(a.comp);
+  if (a.d2h) cudaStreamDestroy(a.d2h);
+  a = Arena();
+  return GEOT_OK;
+}
+
 int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t *src_index,
                                   const int64_t *dst_index, const void *weight, void *dst, int64_t E, int64_t S,
                                   int64_t H, int64_t F, int dtype, int reduce, int weight_layout) {
@@ -469,49 +518,99 @@ int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t 
   if (E <= 0) return GEOT_ERR_EMPTY;
   if (S <= 0 || H <= 0 || F <= 0 || dtype < GEOT_F32 || dtype > GEOT_F16) return GEOT_ERR_INVALID_ARG;
   if ((weight_layout == GEOT_W_NONE) != (weight == nullptr)) return GEOT_ERR_INVALID_ARG;
+  if (weight_layout == GEOT_W_HEAD_EDGE && H > 1) return GEOT_ERR_UNSUPPORTED;  // [H,E] cannot be sliced by edge
   const int64_t W = H * F;
   const size_t es = dtype_size(dtype);
-  const size_t src_rows = src_index ? (size_t)N_src : (size_t)E;
-  const size_t b_src = src_rows * W * es, b_idx = (size_t)E * 8, b_dst = (size_t)S * W * es;
-  const size_t b_w = weight ? (size_t)E * (weight_layout == GEOT_W_EDGE ? 1 : H) * es : 0;
-  const size_t b_ws = geot_b200_workspace_bytes(E, W, dtype, 1);
-  char *d_base = nullptr;
-  const size_t total = align256(b_src) + 2 * align256(b_idx) + align256(b_w) + align256(b_dst) + align256(b_ws);
-  cudaStream_t st = nullptr, st2 = nullptr;
-  cudaEvent_t ev = nullptr;
-  int rc = GEOT_OK;
-#define HOST_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rc = cuda_fail(e__, #expr); goto done; } } while (0)
-  {
-    HOST_TRY(cudaMalloc(&d_base, total));
-    HOST_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    HOST_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
-    HOST_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    char *p = d_base;
-    void *d_src = p; p += align256(b_src);
-    int64_t *d_di = reinterpret_cast<int64_t *>(p); p += align256(b_idx);
-    int64_t *d_si = reinterpret_cast<int64_t *>(p); p += align256(b_idx);
-    void *d_w = p; p += align256(b_w);
-    void *d_dst = p; p += align256(b_dst);
-    void *d_ws = p;
-    // two copy streams so that both directions of the link and both DMA engines are busy
-    HOST_TRY(cudaMemcpyAsync(d_di, dst_index, b_idx, cudaMemcpyHostToDevice, st));
-    HOST_TRY(cudaMemcpyAsync(d_src, src, b_src, cudaMemcpyHostToDevice, st2));
-    if (src_index) HOST_TRY(cudaMemcpyAsync(d_si, src_index, b_idx, cudaMemcpyHostToDevice, st2));
-    if (weight) HOST_TRY(cudaMemcpyAsync(d_w, weight, b_w, cudaMemcpyHostToDevice, st));
-    HOST_TRY(cudaEventRecord(ev, st2));
-    HOST_TRY(cudaStreamWaitEvent(st, ev, 0));
-    rc = geot_b200_segment_reduce(d_src, src_index ? d_si : nullptr, d_di, weight ? d_w : nullptr, d_dst, E, S, H, F,
-                                  dtype, reduce, weight_layout, 1, nullptr, d_ws, b_ws, st);
-    if (rc != GEOT_OK) goto done;
-    HOST_TRY(cudaMemcpyAsync(dst, d_dst, b_dst, cudaMemcpyDeviceToHost, st));
-    HOST_TRY(cudaStreamSynchronize(st));
+  const size_t wpe = weight ? (weight_layout == GEOT_W_EDGE ? 1 : (size_t)H) * es : 0;   // weight bytes per edge
+  const bool gather = src_index != nullptr;
+  const size_t b_src = (gather ? (size_t)N_src : 0) * W * es;   // index_scatter: src rows are edge-aligned, sliced
+  const size_t src_pe = gather ? 0 : (size_t)W * es;            // src bytes per edge when sliced
+  const size_t b_dst = (size_t)S * W * es;
+
+  // slices: about 128 MB of edge-aligned operands each, at least 4, cut at segment boundaries
+  const size_t per_edge = 8 + (gather ? 8 : 0) + wpe + src_pe;
+  int n_slices = (int)std::min<size_t>(Arena::kMaxSlices, std::max<size_t>(4, ((size_t)E * per_edge) >> 27));
+  if (E < 4096) n_slices = 1;
+  int64_t cut[Arena::kMaxSlices + 1];
+  cut[0] = 0;
+  int ns = 0;
+  for (int k = 1; k <= n_slices; ++k) {
+    int64_t c = (k == n_slices) ? E : (E / n_slices) * k;
+    while (c < E && c > 0 && dst_index[c] == dst_index[c - 1]) ++c;   // move right to a segment boundary
+    if (c > cut[ns]) cut[++ns] = c;
+    if (c >= E) break;
   }
-done:
+  if (cut[ns] != E) cut[++ns] = E;
+  n_slices = ns;
+  int64_t max_slice = 0;
+  for (int k = 0; k < n_slices; ++k) max_slice = std::max(max_slice, cut[k + 1] - cut[k]);
+
+  // double-buffered slice operands + src + dst + workspace
+  const size_t slice_bytes = align256((size_t)max_slice * 8) * (gather ? 2 : 1) + align256((size_t)max_slice * wpe) +
+                             align256((size_t)max_slice * src_pe);
+  const size_t b_ws = geot_b200_workspace_bytes(max_slice, W, dtype, 1);
+  const size_t total = align256(b_src) + align256(b_dst) + 2 * slice_bytes + align256(b_ws);
+  Arena &a = g_arena;
+  int rc = GEOT_OK;
+#define HOST_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return cuda_fail(e__, #expr); } while (0)
+  if (!a.h2d) {
+    HOST_TRY(cudaStreamCreateWithFlags(&a.h2d, cudaStreamNonBlocking));
+    HOST_TRY(cudaStreamCreateWithFlags(&a.comp, cudaStreamNonBlocking));
+    HOST_TRY(cudaStreamCreateWithFlags(&a.d2h, cudaStreamNonBlocking));
+    HOST_TRY(cudaEventCreateWithFlags(&a.src_ready, cudaEventDisableTiming));
+    for (int i = 0; i < Arena::kMaxSlices; ++i) {
+      HOST_TRY(cudaEventCreateWithFlags(&a.copied[i], cudaEventDisableTiming));
+      HOST_TRY(cudaEventCreateWithFlags(&a.reduced[i], cudaEventDisableTiming));
+    }
+  }
+  if (a.bytes < total) {
+    if (a.base) HOST_TRY(cudaFree(a.base));
+    a.base = nullptr; a.bytes = 0;
+    HOST_TRY(cudaMalloc(&a.base, total));
+    a.bytes = total;
+  }
+  char *p = a.base;
+  char *d_src = p; p += align256(b_src);
+  char *d_dst = p; p += align256(b_dst);
+  char *d_slice[2] = {p, p + slice_bytes}; p += 2 * slice_bytes;
+  void *d_ws = p;
+
+  HOST_TRY(cudaMemsetAsync(d_dst, 0, b_dst, a.comp));      // empty rows read 0; slices never clear
+  if (gather) HOST_TRY(cudaMemcpyAsync(d_src, src, b_src, cudaMemcpyHostToDevice, a.h2d));
+  HOST_TRY(cudaEventRecord(a.src_ready, a.h2d));
+  HOST_TRY(cudaStreamWaitEvent(a.comp, a.src_ready, 0));
+
+  for (int k = 0; k < n_slices; ++k) {
+    const int64_t e0 = cut[k], n = cut[k + 1] - cut[k];
+    char *q = d_slice[k & 1];
+    int64_t *s_di = reinterpret_cast<int64_t *>(q); q += align256((size_t)max_slice * 8);
+    int64_t *s_si = nullptr;
+    if (gather) { s_si = reinterpret_cast<int64_t *>(q); q += align256((size_t)max_slice * 8); }
+    char *s_w = q; q += align256((size_t)max_slice * wpe);
+    char *s_x = q;
+    // the buffer is free once slice k-2 has been reduced
+    if (k >= 2) HOST_TRY(cudaStreamWaitEvent(a.h2d, a.reduced[k - 2], 0));
+    HOST_TRY(cudaMemcpyAsync(s_di, dst_index + e0, (size_t)n * 8, cudaMemcpyHostToDevice, a.h2d));
+    if (gather) HOST_TRY(cudaMemcpyAsync(s_si, src_index + e0, (size_t)n * 8, cudaMemcpyHostToDevice, a.h2d));
+    if (weight) HOST_TRY(cudaMemcpyAsync(s_w, static_cast<const char *>(weight) + (size_t)e0 * wpe, (size_t)n * wpe, cudaMemcpyHostToDevice, a.h2d));
+    if (!gather) HOST_TRY(cudaMemcpyAsync(s_x, static_cast<const char *>(src) + (size_t)e0 * src_pe, (size_t)n * src_pe, cudaMemcpyHostToDevice, a.h2d));
+    HOST_TRY(cudaEventRecord(a.copied[k], a.h2d));
+    HOST_TRY(cudaStreamWaitEvent(a.comp, a.copied[k], 0));
+    rc = segment_reduce_impl(gather ? d_src : s_x, s_si, s_di, weight ? s_w : nullptr, d_dst, n, S, H, F, dtype, reduce,
+                             weight_layout, 1, nullptr, d_ws, b_ws, a.comp, /*clear_mode=*/1);
+    if (rc != GEOT_OK) { cudaDeviceSynchronize(); return rc; }
+    HOST_TRY(cudaEventRecord(a.reduced[k], a.comp));
+    // rows [first row of slice k, first row of slice k+1) are final: send them home
+    const int64_t r0 = dst_index[e0], r1 = (k + 1 < n_slices) ? dst_index[cut[k + 1]] : S;
+    HOST_TRY(cudaStreamWaitEvent(a.d2h, a.reduced[k], 0));
+    const int64_t rr0 = (k == 0) ? 0 : r0;
+    HOST_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + (size_t)rr0 * W * es, d_dst + (size_t)rr0 * W * es,
+                             (size_t)(r1 - rr0) * W * es, cudaMemcpyDeviceToHost, a.d2h));
+  }
+  HOST_TRY(cudaStreamSynchronize(a.d2h));
+  HOST_TRY(cudaStreamSynchronize(a.comp));
+  HOST_TRY(cudaStreamSynchronize(a.h2d));
 #undef HOST_TRY
-  if (ev) cudaEventDestroy(ev);
-  if (st) cudaStreamDestroy(st);
-  if (st2) cudaStreamDestroy(st2);
-  if (d_base) cudaFree(d_base);
   return rc;
 }
 

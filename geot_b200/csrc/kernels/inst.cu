@@ -54,7 +54,9 @@ cudaError_t launch_shape(const Params &p, const Shape &sh, cudaStream_t stream) 
     }
   } else if (sh.lpr == 32) {
     if (sh.vpl == 2) return launch_one<T, VECW, 32, 2, RED>(p, sh, stream);
-    if (sh.vpl == 4) return launch_one<T, VECW, 32, 4, RED>(p, sh, stream);
+    if constexpr (VECW <= 4) {   // 8-element vectors stop at 2 per lane (accumulator registers)
+      if (sh.vpl == 4) return launch_one<T, VECW, 32, 4, RED>(p, sh, stream);
+    }
   }
   return cudaErrorInvalidValue;
 }

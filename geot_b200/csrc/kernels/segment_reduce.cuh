@@ -131,7 +131,7 @@ template <> __device__ __forceinline__ float ld_stream_t<float>(const float *p, 
 #endif
 
 template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
-__global__ void __launch_bounds__(kThreads, (VPL == 1 ? GEOT_MINB : (VPL == 2 ? 2 : 1)))
+__global__ void __launch_bounds__(kThreads, (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1)))
 segment_reduce_kernel(const Params p) {
   using A = typename AccOf<T>::type;
   using VecT = Vec<T, VECW>;
@@ -191,13 +191,24 @@ segment_reduce_kernel(const Params p) {
   const int64_t row_bytes = W * (int64_t)sizeof(T);
 
   A acc[VPL][VECW];    // the open run
-  A hacc[VPL][VECW];   // the chunk's HEAD partial, once closed
 #pragma unroll
   for (int j = 0; j < VPL; ++j)
 #pragma unroll
-    for (int i = 0; i < VECW; ++i) { acc[j][i] = red_identity<RED, A>(); hacc[j][i] = red_identity<RED, A>(); }
-  long long cnt = 0, hcnt = 0;
+    for (int i = 0; i < VECW; ++i) acc[j][i] = red_identity<RED, A>();
+  long long cnt = 0;
   int flags = 0;
+
+  // parks a partial in this group's shared-memory slot (private to the group until the barrier)
+  auto park = [&](A *slot, long long *slot_cnt, int64_t *slot_row, int64_t row) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      Vec<A, VECW> t;
+#pragma unroll
+      for (int i = 0; i < VECW; ++i) t.v[i] = acc[j][i];
+      *reinterpret_cast<Vec<A, VECW> *>(slot + g * CW + (j * LPR + gl) * VECW) = t;
+    }
+    if (gl == 0) { slot_cnt[g] = cnt; slot_row[g] = row; }
+  };
 
   auto finalize_store = [&](int64_t row, A(&a)[VPL][VECW], long long n) {
 #pragma unroll
@@ -223,11 +234,7 @@ segment_reduce_kernel(const Params p) {
     // closes the open run, whose row is `row`
     auto close_run = [&](int64_t row) {
       if (is_head) {
-#pragma unroll
-        for (int j = 0; j < VPL; ++j)
-#pragma unroll
-          for (int i = 0; i < VECW; ++i) hacc[j][i] = acc[j][i];
-        hcnt = cnt;
+        park(s_head, s_head_cnt, s_head_row, row);
         flags |= FLAG_HEAD;
         is_head = false;
       } else {
@@ -279,6 +286,10 @@ segment_reduce_kernel(const Params p) {
       const unsigned bmask = (__ballot_sync(gmask, gl < nb && my_dst != left) >> gshift) & low_bits<LPR>();
       const int64_t batch_left = last_dst;
       last_dst = __shfl_sync(gmask, my_dst, nb - 1, LPR);
+      const T *wb[VPL];                 // WM_GENERIC: this batch's weights for this lane's heads
+      const int ws_e32 = (int)p.ws_e;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) wb[j] = (WM == WM_GENERIC && lane_w[j] != nullptr) ? lane_w[j] + b * p.ws_e : nullptr;
 
       if (nb == LPR) {
         // ---- full batch: U loads in flight, branch-free when the U edges hold no segment head ----
@@ -294,7 +305,7 @@ segment_reduce_kernel(const Params p) {
             for (int j = 0; j < VPL; ++j) {
               v[u][j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
               w[u][j] = we;
-              if (WM == WM_GENERIC && lane_w[j] != nullptr) w[u][j] = to_acc<T>(__ldg(lane_w[j] + (b + k0 + u) * p.ws_e));
+              if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
             }
           }
           const unsigned sub = (bmask >> k0) & low_bits<U>();
@@ -327,7 +338,7 @@ segment_reduce_kernel(const Params p) {
           for (int j = 0; j < VPL; ++j) {
             v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
             w[j] = we;
-            if (WM == WM_GENERIC && lane_w[j] != nullptr) w[j] = to_acc<T>(__ldg(lane_w[j] + (b + k) * p.ws_e));
+            if (WM == WM_GENERIC && wb[j] != nullptr) w[j] = to_acc<T>(__ldg(wb[j] + k * ws_e32));
           }
           if ((bmask >> k) & 1u) close_run(k == 0 ? batch_left : row);
           accumulate(v, w);
@@ -341,28 +352,13 @@ segment_reduce_kernel(const Params p) {
     const int64_t cur_row = last_dst;
     const bool continues = (cur_row == next_row);
     if (is_head) {                      // the whole chunk is one run that entered from the left
-#pragma unroll
-      for (int j = 0; j < VPL; ++j)
-#pragma unroll
-        for (int i = 0; i < VECW; ++i) hacc[j][i] = acc[j][i];
-      hcnt = cnt;
+      park(s_head, s_head_cnt, s_head_row, cur_row);
       flags |= FLAG_HEAD | (continues ? FLAG_THROUGH : 0);
     } else if (continues) {
-#pragma unroll
-      for (int j = 0; j < VPL; ++j)
-#pragma unroll
-        for (int i = 0; i < VECW; ++i) s_tail[g * CW + (j * LPR + gl) * VECW + i] = acc[j][i];
-      if (gl == 0) { s_tail_cnt[g] = cnt; s_tail_row[g] = cur_row; }
+      park(s_tail, s_tail_cnt, s_tail_row, cur_row);
       flags |= FLAG_TAIL;
     } else {
       finalize_store(cur_row, acc, cnt);
-    }
-    if (flags & FLAG_HEAD) {
-#pragma unroll
-      for (int j = 0; j < VPL; ++j)
-#pragma unroll
-        for (int i = 0; i < VECW; ++i) s_head[g * CW + (j * LPR + gl) * VECW + i] = hacc[j][i];
-      if (gl == 0) { s_head_cnt[g] = hcnt; s_head_row[g] = prev_row; }
     }
   }
   if (gl == 0) s_flags[g] = flags;

@@ -153,15 +153,17 @@ GEOT_API int geot_b200_mh_spmm(const void *src, const int64_t *src_index, const 
 
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------------- */
 
-/* Same operation with every operand in HOST memory (pinned memory makes the copies asynchronous):
- * stages the operands to the device in edge chunks on two streams so that the copy of chunk i+1
- * overlaps the reduction of chunk i, reduces, and copies dst back.  Allocates and frees its own
- * device buffers; returns after dst is complete in host memory.  S must be given.  This is the call
- * a non-torch host (cgo / JNI / ctypes) makes. */
+/* Same operation with every operand in HOST memory (pinned memory makes the copies asynchronous).
+ * src is copied first, then the sorted edge list in slices cut at segment boundaries: slice k+1 is
+ * copied while slice k is reduced and the finished dst rows of slice k-1 travel back.  Device buffers
+ * come from a per-process arena that is reused across calls (geot_b200_host_arena_release frees it).
+ * Returns after dst is complete in host memory.  dst_index must be sorted; S must be given.  Not
+ * thread-safe (one arena).  This is the call a non-torch host (cgo / JNI / ctypes) makes. */
 GEOT_API int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t *src_index,
                                   const int64_t *dst_index, const void *weight, void *dst,
                                   int64_t E, int64_t S, int64_t H, int64_t F, int dtype, int reduce,
                                   int weight_layout);
+GEOT_API int geot_b200_host_arena_release(void);
 
 /* ---- instrumentation -------------------------------------------------------------------------- */
 

@@ -366,6 +366,28 @@ def test_non_default_stream_and_host_entry():
     assert_close(out, oracle.segment_reduce(src, si, di, w, "max"), torch.float32, "max", "host entry max")
 
 
+def test_host_entry_pipeline_slices():
+    """The host-buffer entry cuts the edge list into slices at segment boundaries (>= 4 slices once
+    E >= 4096): hubs, gaps and every op shape must survive the slicing."""
+    si, di, g = make_graph(300000, 900, seed=33, skew=0.5, hub=0.3, gaps=True)
+    E = di.numel()
+    S = int(di[-1]) + 1
+    w = torch.rand(E, generator=g)
+    src = torch.rand(900, 64, generator=g)
+    for red in ("sum", "mean", "min"):
+        out = abi.segment_reduce_host(src, si, di, w, red, S=S)
+        assert_close(out, oracle.segment_reduce(src, si, di, w, red, S=S, acc64=red != "min"), torch.float32, red, "host gws " + red)
+    srcE = torch.rand(E, 24, generator=g)                       # index_scatter: src is sliced with the edges
+    out = abi.segment_reduce_host(srcE, None, di, None, "sum", S=S + 5)
+    assert_close(out, oracle.segment_reduce(srcE, None, di, None, "sum", S=S + 5, acc64=True), torch.float32, "sum", "host index_scatter")
+    H = 4
+    wh = torch.rand(E, H, generator=g).bfloat16()
+    xh = torch.rand(900, H, 16, generator=g).bfloat16()
+    out = abi.segment_reduce_host(xh, si, di, wh, "sum", S=S, H=H)
+    assert_close(out, oracle.mh_spmm(si, di, wh, xh), torch.bfloat16, "sum", "host mh_spmm")
+    assert abi.lib().geot_b200_host_arena_release() == 0
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference's own CUDA kernels on this GPU (oracle/_ref, built from /root/reference unmodified)
 # ------------------------------------------------------------------------------------------------

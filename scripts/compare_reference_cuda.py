@@ -1,0 +1,95 @@
+"""Times the reference's own CUDA kernels (oracle/_ref/geot_ref_C.so: GeoT csrc/ recompiled unmodified for
+sm_100) beside this repo's operators on the BASELINE shapes, same inputs, same GPU, CUDA events.
+
+Both sides are timed as the drop-in call a user makes (torch.ops.geot_ref.* vs geot_b200.*: allocation,
+plan lookup / index[-1].item() included) and this repo additionally through the C ABI with a cached plan
+and preallocated output ("kernel-only").  Bench support, not product.  Writes one JSON line per workload.
+
+    python scripts/compare_reference_cuda.py [workload ...] > gpurun_out/compare_reference.jsonl
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+import geot_b200  # noqa: E402
+import oracle  # noqa: E402
+from geot_b200 import abi  # noqa: E402
+
+
+def timed(fn, warmup=3, iters=10):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def main():
+    names = sys.argv[1:] or ["config1_index_scatter", "reddit_gws", "products_gs64", "products_gs256", "proteins_gws256",
+                             "arxiv_mh_spmm"]
+    have_ref = oracle.load_ref_extension()
+    for name in names:
+        wk = bench.build_workload(name, "cuda")
+        op, x, w, si, di, S, H = wk["op"], wk["x"], wk["w"], wk["si"], wk["di"], wk["S"], wk["H"]
+        if wk["dtype"] != torch.float32:          # the reference CUDA path is fp32/fp64 only
+            x32, w32 = x.float(), (w.float() if w is not None else None)
+        else:
+            x32, w32 = x, w
+        if op == "index_scatter":
+            ours = lambda: geot_b200.index_scatter(0, x, di, "sum", True)
+            ref = lambda: torch.ops.geot_ref.index_scatter(0, di, x32, "sum", True)
+            ref_valid = wk["E"] * wk["F"] < 2 ** 31      # int overflow in the reference beyond
+        elif op == "gather_scatter":
+            ours = lambda: geot_b200.gather_scatter(si, di, x)
+            ref = lambda: torch.ops.geot_ref.gather_scatter_impl(si, di, x32)
+            ref_valid = True
+        elif op == "gather_weight_scatter":
+            ours = lambda: geot_b200.gather_weight_scatter(si, di, w, x)
+            ref = lambda: torch.ops.geot_ref.gather_weight_scatter_impl(si, di, w32, x32)
+            ref_valid = True
+        else:
+            ours = lambda: geot_b200.mh_spmm(si, di, w, x)
+            ref = lambda: torch.ops.geot_ref.mh_spmm(si, di, w32, x32, "sum")
+            ref_valid = True
+        layout = abi.W_NONE if w is None else (abi.W_EDGE if w.dim() == 1 else abi.W_EDGE_HEAD)
+        plan = abi.DevicePlan(di, S)
+        ws = abi.Workspace(wk["E"], wk["F"] * H, wk["dtype"], "cuda")
+        out = torch.empty([S] + list(x.shape[1:]), dtype=wk["dtype"], device="cuda")
+        kern = lambda: abi.segment_reduce(x, si, di, w, "sum", S=S, H=H, weight_layout=layout, plan=plan, out=out, workspace=ws)
+        rec = {"workload": name, "E": wk["E"], "S": S, "F": wk["F"], "H": H, "dtype": bench.DTYPE_NAME[wk["dtype"]],
+               "bytes_logical": wk["bytes_logical"]}
+        b, m = timed(kern)
+        rec["ours_abi_cached_plan_ms"] = {"best": round(b, 4), "median": round(m, 4)}
+        rec["ours_abi_GBps_logical"] = round(wk["bytes_logical"] / b / 1e6, 1)
+        b2, m2 = timed(ours)
+        rec["ours_dropin_call_ms"] = {"best": round(b2, 4), "median": round(m2, 4)}
+        if have_ref and ref_valid:
+            try:
+                rb, rm = timed(ref, warmup=2, iters=5)
+                rec["reference_cuda_dropin_call_ms"] = {"best": round(rb, 4), "median": round(rm, 4)}
+                rec["reference_cuda_GBps_logical"] = round(wk["bytes_logical"] / rb / 1e6, 1)
+                rec["speedup_dropin_vs_reference"] = round(rb / b2, 2)
+                rec["speedup_kernel_vs_reference"] = round(rb / b, 2)
+                a, r = ours().float(), ref()
+                rec["max_rel_diff_vs_reference"] = float(((a - r).abs() / r.abs().clamp_min(1e-30)).max())
+                rec["reference_dtype"] = "f32"
+            except Exception as e:  # noqa: BLE001
+                rec["reference_error"] = str(e)[:200]
+        else:
+            rec["reference_cuda"] = "not run: " + ("int overflow (nnz*F >= 2^31)" if have_ref else "oracle/_ref not built")
+        print(json.dumps(rec), flush=True)
+        del wk, x, w, si, di, plan, ws, out, x32, w32
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -273,9 +273,11 @@ def run_own(args):
     ws = abi.Workspace(l_E, W, wk["dtype"], dev)
     out = torch.empty([l_S] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device=dev)
 
+    x_full = torch.empty([N] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device=dev) if (world > 1 and wk["op"] != "index_scatter") else None
+
     def step():
         if world > 1 and wk["op"] != "index_scatter":
-            xf = gdist.all_gather_rows(x_local, rb)
+            xf = gdist.all_gather_rows(x_local, rb, out=x_full)
         elif world > 1:
             xf = l_x_edges
         else:

@@ -2,7 +2,7 @@
 
 Same Python surface as the reference package (``/root/reference/geot/__init__.py:4-9``) for the hot
 path: ``index_scatter``, ``gather_scatter``, ``gather_weight_scatter``, ``mh_spmm``,
-``mh_spmm_transposed``; plus ``format_preprocess`` (segment pointers + edge-count partition) and
+``mh_spmm_transposed``, ``csr_gws``, ``coo_to_csr``; plus ``format_preprocess`` (segment pointers + edge-count partition) and
 ``dist`` (dst-row sharding over the GPUs of one box).  The operators are ``torch.ops.geot.*``
 registered by ``geot_b200/_C.so`` (thin bindings over the C ABI in ``include/geot_b200.h``).
 
@@ -35,8 +35,11 @@ from .index_scatter import index_scatter  # noqa: E402
 from .gather_scatter import gather_scatter  # noqa: E402
 from .gather_weight_scatter import gather_weight_scatter  # noqa: E402
 from .mh_spmm import mh_spmm, mh_spmm_transposed  # noqa: E402
-from .format_preprocess import format_preprocess, Plan, coo_to_csr, clear_plan_cache  # noqa: E402
+from .gather_weight_scatter import sddmm_coo_impl  # noqa: E402
+from .csr_gws import csr_gws, coo_to_csr  # noqa: E402
+from .format_preprocess import format_preprocess, Plan, clear_plan_cache  # noqa: E402
+from . import fake as _fake  # noqa: E402,F401  (register_fake for the C++-registered operators)
 from . import dist  # noqa: E402
 
-__all__ = ["index_scatter", "gather_scatter", "gather_weight_scatter", "mh_spmm", "mh_spmm_transposed",
-           "format_preprocess", "Plan", "coo_to_csr", "clear_plan_cache", "dist"]
+__all__ = ["index_scatter", "gather_scatter", "gather_weight_scatter", "mh_spmm", "mh_spmm_transposed", "csr_gws",
+           "coo_to_csr", "sddmm_coo_impl", "format_preprocess", "Plan", "clear_plan_cache", "dist"]

@@ -22,6 +22,7 @@ SYMBOLS = [
     "geot_b200_index_last", "geot_b200_plan_bytes", "geot_b200_format_preprocess", "geot_b200_plan_shards",
     "geot_b200_workspace_bytes", "geot_b200_segment_reduce", "geot_b200_index_scatter",
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
+    "geot_b200_sddmm_coo", "geot_b200_csr_to_coo",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
 ]
 
@@ -61,6 +62,8 @@ def lib() -> ctypes.CDLL:
                                                       ctypes.POINTER(GeotPlan), vp, sz, vp]
         L.geot_b200_mh_spmm.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci,
                                         ctypes.POINTER(GeotPlan), vp, sz, vp]
+        L.geot_b200_sddmm_coo.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, vp]
+        L.geot_b200_csr_to_coo.argtypes = [vp, ci, i64, i64, vp, vp]
         L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
         _lib = L
     return _lib
@@ -150,6 +153,23 @@ def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H
         REDUCE[reduce], weight_layout, 1 if sorted else 0, ctypes.byref(plan.c) if plan is not None else None,
         _ptr(workspace.buf), workspace.nbytes, _stream())
     check(st, "segment_reduce")
+    return out
+
+
+def sddmm_coo(mat1, row_index, mat2, col_index):
+    """out[e] = <mat1[row_index[e]], mat2[col_index[e]]> through geot_b200_sddmm_coo."""
+    E = row_index.numel()
+    out = torch.empty(E, dtype=mat1.dtype, device=mat1.device)
+    check(lib().geot_b200_sddmm_coo(_ptr(mat1), _ptr(row_index), _ptr(mat2), _ptr(col_index), _ptr(out), E,
+                                    mat1.shape[1], DTYPE[mat1.dtype], _stream()), "sddmm_coo")
+    return out
+
+
+def csr_to_coo(rowptr, E):
+    """Sorted COO row index [E] (int64) of a CSR row pointer (int32 or int64) through geot_b200_csr_to_coo."""
+    out = torch.empty(E, dtype=torch.int64, device=rowptr.device)
+    bits = 64 if rowptr.dtype == torch.int64 else 32
+    check(lib().geot_b200_csr_to_coo(_ptr(rowptr), bits, rowptr.numel() - 1, E, _ptr(out), _stream()), "csr_to_coo")
     return out
 
 

@@ -56,6 +56,10 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok)
   if (nvec <= 32) {
     lpr = pow2ceil(nvec);
     vpl = 1;
+    // experiment knob: narrower groups sweep the row in column slabs (the slab is the slow grid index), which
+    // shrinks the gathered working set per sweep at the price of re-reading the index streams
+    const int cap = env_int("GEOT_B200_LPR", 0);
+    if (cap >= 1 && cap < lpr) lpr = pow2ceil(cap);
   } else {
     // wider rows: several vectors per lane, capped so that the accumulators stay within 16 registers
     // (fp32: 4 vectors, fp64: 4, bf16/fp16 with 8-element vectors: 2); beyond that, column tiles
@@ -67,6 +71,11 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok)
   c.shape.lpr = lpr;
   c.shape.vpl = vpl;
   c.shape.col_tiles = (int)((nvec + (int64_t)lpr * vpl - 1) / ((int64_t)lpr * vpl));
+  c.shape.wm = 0;
+  // cp.async ring depth (sub-batches in flight per group) for the kernels that have one (sum, 16-byte vectors,
+  // rows of >= 8 vectors): 3 for 256-byte rows, 2 otherwise -- profiles/r01_ring_sweep.md.  GEOT_B200_RING=0
+  // selects the register path, another value a depth a tuning build carries.
+  c.shape.pf = env_int("GEOT_B200_RING", (vecw > 1 && lpr >= 8) ? (lpr == 16 ? 3 : 2) : 0);
   const int ng = geot::kThreads / lpr;
   // Edge-count partition: every group owns `chunk` consecutive edges.  Longer chunks amortise the
   // per-chunk carry handling; shorter ones keep small inputs spread over all 148 SMs.
@@ -199,6 +208,20 @@ __global__ void gather_index_kernel(const int64_t *__restrict__ perm, const int6
   if (i < n) out[i] = in[perm[i]];
 }
 
+// CSR row pointer -> COO row index: one thread per edge, binary search of the edge position in rowptr
+// (upper bound - 1).  Rows are found independently, so the kernel is a single coalesced write pass.
+template <typename P>
+__global__ void csr_rows_kernel(const P *__restrict__ rowptr, int64_t S, int64_t E, int64_t *__restrict__ row) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t lo = 0, hi = S;   // last r with rowptr[r] <= e
+  while (hi - lo > 1) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if ((int64_t)rowptr[mid] <= e) lo = mid; else hi = mid;
+  }
+  row[e] = lo;
+}
+
 // ---- instrumentation: event pairs around the main kernel ------------------------------------------
 struct Profile {
   int n = 0;
@@ -216,6 +239,11 @@ int bits_for(int64_t S) { int b = 1; while (b < 63 && ((int64_t)1 << b) < S) ++b
 
 // ==================================================================================================
 extern "C" {
+
+// used by the other translation units of the library (sddmm.cu); not exported
+__attribute__((visibility("hidden"))) int geot_b200_set_cuda_error(const char *what, int cuda_error) {
+  return cuda_fail((cudaError_t)cuda_error, what);
+}
 
 int geot_b200_version(void) { return GEOT_B200_VERSION; }
 int geot_b200_arch(void) { return 100; }
@@ -287,6 +315,17 @@ int geot_b200_plan_shards(const geot_plan_t *plan, int parts, int64_t *row_bound
   CUDA_TRY(cudaMemcpyAsync(row_bounds, d_bounds, (parts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaMemcpyAsync(edge_bounds, d_bounds + (kMaxParts + 1), (parts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
+  return GEOT_OK;
+}
+
+int geot_b200_csr_to_coo(const void *rowptr, int rowptr_bits, int64_t S, int64_t E, int64_t *row_index,
+                         cudaStream_t stream) {
+  if (!rowptr || !row_index || S <= 0 || E < 0 || (rowptr_bits != 32 && rowptr_bits != 64)) return GEOT_ERR_INVALID_ARG;
+  if (E == 0) return GEOT_OK;
+  const unsigned nb = (unsigned)((E + 255) / 256);
+  if (rowptr_bits == 64) csr_rows_kernel<int64_t><<<nb, 256, 0, stream>>>(static_cast<const int64_t *>(rowptr), S, E, row_index);
+  else csr_rows_kernel<int32_t><<<nb, 256, 0, stream>>>(static_cast<const int32_t *>(rowptr), S, E, row_index);
+  CUDA_TRY(cudaGetLastError());
   return GEOT_OK;
 }
 

@@ -124,15 +124,19 @@ geot_plan_t get_plan(const at::Tensor &dst_index, at::Tensor *keepalive) {
   return plan;
 }
 
+void clear_csr_cache();
 void clear_plan_cache() {
-  std::lock_guard<std::mutex> lk(g_plan_mu);
-  g_plans.clear();
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    g_plans.clear();
+  }
+  clear_csr_cache();
 }
 
 // ---- the one call every op funnels into ---------------------------------------------------------------
 at::Tensor run(const char *what, const at::Tensor &src_in, const c10::optional<at::Tensor> &src_index_in,
                const at::Tensor &dst_index_in, const c10::optional<at::Tensor> &weight_in, int64_t H, int64_t F,
-               int reduce, int weight_layout, bool sorted, std::vector<int64_t> out_shape) {
+               int reduce, int weight_layout, bool sorted, std::vector<int64_t> out_shape, int64_t min_rows = 0) {
   c10::cuda::CUDAGuard guard(src_in.device());
   TORCH_CHECK(src_in.is_cuda(), "geot::", what, ": src must be a CUDA tensor (this build has no CPU path)");
   check_index(dst_index_in, "index");
@@ -167,8 +171,11 @@ at::Tensor run(const char *what, const at::Tensor &src_in, const c10::optional<a
   } else {
     S = dst_index.max().item<int64_t>() + 1;
   }
-  out_shape[0] = S;
+  // min_rows > S: the caller wants trailing rows that no edge reaches (csr_gws); they are zero-filled here and the
+  // kernels see the [S, W] prefix
+  out_shape[0] = std::max(S, min_rows);
   at::Tensor out = at::empty(out_shape, src.options());
+  if (min_rows > S) out.narrow(0, S, min_rows - S).zero_();
   const int64_t W = H * F;
   const size_t ws_bytes = geot_b200_workspace_bytes(E, W, dtype, sorted ? 1 : 0);
   at::Tensor ws = at::empty({(int64_t)ws_bytes}, src.options().dtype(at::kByte));
@@ -270,6 +277,103 @@ at::Tensor plan_shards(at::Tensor dst_index, int64_t parts) {
   return out;
 }
 
+// geot::sddmm_coo_impl -- csrc/gather_weight_scatter.cpp:36-44 + csrc/cuda/gather_weight_scatter_cuda.cu:41-62:
+// out[e] = <mat_1[dst_index[e]], mat_2[src_index[e]]> (row = dst_index, col = src_index).  The reference
+// narrows the indices to int32 and is fp32 only; here int64 / int32 indices and all four dtypes.
+at::Tensor sddmm_coo_impl(at::Tensor src_index, at::Tensor dst_index, at::Tensor mat_1, at::Tensor mat_2) {
+  TORCH_CHECK(mat_1.is_cuda() && mat_2.is_cuda(), "geot::sddmm_coo: mat_1 and mat_2 must be CUDA tensors (this build has no CPU path)");
+  TORCH_CHECK(src_index.dim() == 1 && dst_index.dim() == 1 && src_index.numel() == dst_index.numel(),
+              "src_index and dst_index must be 1 dimensional and of the same length");
+  TORCH_CHECK(mat_1.dim() == 2 && mat_2.dim() == 2 && mat_1.size(1) == mat_2.size(1), "mat_1 and mat_2 must be 2 dimensional with the same width");
+  TORCH_CHECK(mat_1.scalar_type() == mat_2.scalar_type(), "mat_1 and mat_2 must have the same dtype");
+  c10::cuda::CUDAGuard guard(mat_1.device());
+  const at::Tensor col = src_index.to(at::kLong).contiguous(), row = dst_index.to(at::kLong).contiguous();
+  TORCH_CHECK(row.is_cuda() && col.is_cuda(), "geot::sddmm_coo: indices must be CUDA tensors");
+  const at::Tensor a = mat_1.contiguous(), b = mat_2.contiguous();
+  at::Tensor out = at::empty({row.numel()}, a.options());
+  check_status(geot_b200_sddmm_coo(a.data_ptr(), row.data_ptr<int64_t>(), b.data_ptr(), col.data_ptr<int64_t>(), out.data_ptr(),
+                                   row.numel(), a.size(1), dtype_enum(a), at::cuda::getCurrentCUDAStream()),
+               "sddmm_coo");
+  return out;
+}
+
+// ---- CSR entry point ------------------------------------------------------------------------------------
+// Cache of the COO row index expanded from a CSR row pointer, keyed like the plans (storage + version).
+struct CsrEntry {
+  explicit CsrEntry(c10::weak_intrusive_ptr<c10::StorageImpl> s) : storage(std::move(s)) {}
+  c10::weak_intrusive_ptr<c10::StorageImpl> storage;
+  const void *storage_raw;
+  int64_t offset, numel, E;
+  uint32_t version;
+  at::Tensor row_index;
+};
+std::list<CsrEntry> g_csr;
+
+at::Tensor csr_row_index(const at::Tensor &indptr, int64_t E) {
+  c10::StorageImpl *raw = indptr.storage().unsafeGetStorageImpl();
+  const uint32_t ver = version_of(indptr);
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto it = g_csr.begin(); it != g_csr.end(); ++it) {
+      if (it->storage_raw == raw && it->offset == indptr.storage_offset() && it->numel == indptr.numel() && it->E == E &&
+          it->version == ver && !it->storage.expired()) {
+        g_csr.splice(g_csr.begin(), g_csr, it);
+        return it->row_index;
+      }
+    }
+  }
+  at::Tensor row = at::empty({E}, indptr.options().dtype(at::kLong));
+  check_status(geot_b200_csr_to_coo(indptr.data_ptr(), indptr.scalar_type() == at::kLong ? 64 : 32, indptr.numel() - 1, E,
+                                    row.data_ptr<int64_t>(), at::cuda::getCurrentCUDAStream()),
+               "csr_to_coo");
+  CsrEntry e(indptr.storage().getWeakStorageImpl());
+  e.storage_raw = raw; e.offset = indptr.storage_offset(); e.numel = indptr.numel(); e.E = E; e.version = ver; e.row_index = row;
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_csr.push_front(std::move(e));
+  while (g_csr.size() > kMaxPlans) g_csr.pop_back();
+  return row;
+}
+
+void clear_csr_cache() {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_csr.clear();
+}
+
+// geot::csr_gws_impl -- csrc/csr_gws.cpp:24-35 + csrc/cuda/csr_gws_cuda.cu: out[r] = sum_{e in row r} weight[e] * src[indices[e]].
+// Like the reference the output has indptr.size(0) rows (= nrow + 1, csr_gws.cpp:29-31); the last one is 0.
+// The row index is expanded from indptr once per graph (cached) and the COO kernels do the rest.
+at::Tensor csr_gws_impl(at::Tensor indptr, at::Tensor indices, at::Tensor weight, at::Tensor src) {
+  TORCH_CHECK(src.is_cuda(), "geot::csr_gws: src must be a CUDA tensor (this build has no CPU path)");
+  TORCH_CHECK(indptr.dim() == 1 && indices.dim() == 1 && indptr.numel() >= 2, "indptr and indices must be 1 dimensional");
+  TORCH_CHECK(src.dim() == 2, "src must be 2 dimensional");
+  TORCH_CHECK(weight.dim() == 1 && weight.numel() == indices.numel(), "weight must be 1 dimensional with one entry per nonzero");
+  TORCH_CHECK(indptr.scalar_type() == at::kLong || indptr.scalar_type() == at::kInt, "indptr must be int32 or int64");
+  c10::cuda::CUDAGuard guard(src.device());
+  const at::Tensor ptr = indptr.contiguous();
+  const int64_t E = indices.numel(), nrow = ptr.numel() - 1;
+  auto shape = src.sizes().vec();
+  shape[0] = nrow + 1;
+  if (E == 0) return at::zeros(shape, src.options());
+  const at::Tensor row = csr_row_index(ptr, E);
+  const at::Tensor col = indices.scalar_type() == at::kLong ? indices : indices.to(at::kLong);
+  // rows after the last non-empty one (at least the reference's extra row) are 0
+  return run("csr_gws", src, col, row, weight, 1, src.size(1), GEOT_SUM, GEOT_W_EDGE, true, src.sizes().vec(), nrow + 1);
+}
+
+// geot::coo_to_csr_impl -- geot/match_replace/format_transform.py:5-18: int32 rowptr [nrow+1], nrow = coo_row.max()+1.
+at::Tensor coo_to_csr_impl(at::Tensor coo_row) {
+  TORCH_CHECK(coo_row.is_cuda(), "geot::coo_to_csr: coo_row must be a CUDA tensor");
+  TORCH_CHECK(coo_row.dim() == 1 && coo_row.numel() > 0, "coo_row must be 1 dimensional and non-empty");
+  c10::cuda::CUDAGuard guard(coo_row.device());
+  at::Tensor idx = (coo_row.scalar_type() == at::kLong ? coo_row : coo_row.to(at::kLong)).contiguous();
+  at::Tensor buf;
+  geot_plan_t plan = get_plan(idx, &buf);
+  TORCH_CHECK(plan.is_sorted, "geot::coo_to_csr: coo_row is not sorted");
+  at::Tensor rowptr = at::from_blob(const_cast<int64_t *>(plan.rowptr), {plan.S + 1}, [buf](void *) mutable { buf.reset(); },
+                                    idx.options());
+  return rowptr.to(at::kInt);
+}
+
 }  // namespace
 
 TORCH_LIBRARY_FRAGMENT(geot, m) {
@@ -278,6 +382,9 @@ TORCH_LIBRARY_FRAGMENT(geot, m) {
   m.def("gather_scatter_impl(Tensor src_index, Tensor dst_index, Tensor src) -> Tensor");
   m.def("gather_weight_scatter_impl(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src) -> Tensor");
   m.def("mh_spmm(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src, str reduce) -> Tensor");
+  m.def("sddmm_coo_impl(Tensor src_index, Tensor dst_index, Tensor mat_1, Tensor mat_2) -> Tensor");
+  m.def("csr_gws_impl(Tensor indptr, Tensor indices, Tensor weight, Tensor src) -> Tensor");
+  m.def("coo_to_csr_impl(Tensor coo_row) -> Tensor");
   // additions: reduce-aware gather ops, the plan, the multi-GPU partition
   m.def("gather_scatter_reduce(Tensor src_index, Tensor dst_index, Tensor src, str reduce) -> Tensor");
   m.def("gather_weight_scatter_reduce(Tensor src_index, Tensor dst_index, Tensor weight, Tensor src, str reduce) -> Tensor");
@@ -292,6 +399,9 @@ TORCH_LIBRARY_IMPL(geot, CUDA, m) {
   m.impl("gather_scatter_impl", gather_scatter_impl);
   m.impl("gather_weight_scatter_impl", gather_weight_scatter_impl);
   m.impl("mh_spmm", mh_spmm_impl);
+  m.impl("sddmm_coo_impl", sddmm_coo_impl);
+  m.impl("csr_gws_impl", csr_gws_impl);
+  m.impl("coo_to_csr_impl", coo_to_csr_impl);
   m.impl("gather_scatter_reduce", gather_scatter_reduce);
   m.impl("gather_weight_scatter_reduce", gather_weight_scatter_reduce);
   m.impl("format_preprocess", format_preprocess);

@@ -10,13 +10,10 @@
 namespace geot {
 namespace {
 
-template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
-cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
-  using A = typename AccOf<T>::type;
-  constexpr int NG = kThreads / LPR;
-  constexpr int CW = LPR * VPL * VECW;
-  constexpr size_t smem = 2 * (size_t)NG * CW * sizeof(A) + (size_t)NG * (4 * 8 + 4);
-  auto kern = segment_reduce_kernel<T, VECW, LPR, VPL, RED, WM>;
+template <typename T, int VECW, int LPR, int VPL, int RED, int WM, int PF>
+cudaError_t launch_pf(const Params &p, const Shape &sh, cudaStream_t stream) {
+  constexpr size_t smem = ShapeOf<T, VECW, LPR, VPL, PF>::smem_bytes;
+  auto kern = segment_reduce_kernel<T, VECW, LPR, VPL, RED, WM, PF>;
   if (smem > 48 * 1024) {
     static bool configured = false;   // per instantiation
     if (!configured) {
@@ -29,6 +26,34 @@ cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
   kern<<<(unsigned)blocks, kThreads, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+// Ring depths built: GEOT_PF_A / _B / _C (production: 2 and 3, the depths abi.cu selects; tuning builds override).
+// The ring needs 16-byte pieces, a sub-batch that fits PF times into a batch, and serves the sum kernels.
+#ifndef GEOT_PF_A
+#define GEOT_PF_A 2
+#define GEOT_PF_B 3
+#endif
+template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
+cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
+  if constexpr (RED == RED_SUM && WM != WM_GENERIC && VECW * sizeof(T) == 16 && LPR >= 8) {
+    constexpr int U = ShapeOf<T, VECW, LPR, VPL, 1>::U;   // ring sub-batch
+    constexpr int PFMAX = LPR / U;
+    constexpr int PFA = GEOT_PF_A < PFMAX ? GEOT_PF_A : PFMAX;
+    if (sh.pf == GEOT_PF_A && ShapeOf<T, VECW, LPR, VPL, PFA>::max_blocks >= 1)
+      return launch_pf<T, VECW, LPR, VPL, RED, WM, PFA>(p, sh, stream);
+#ifdef GEOT_PF_B
+    constexpr int PFB = GEOT_PF_B < PFMAX ? GEOT_PF_B : PFMAX;
+    if (sh.pf == GEOT_PF_B && ShapeOf<T, VECW, LPR, VPL, PFB>::max_blocks >= 1)
+      return launch_pf<T, VECW, LPR, VPL, RED, WM, PFB>(p, sh, stream);
+#endif
+#ifdef GEOT_PF_C
+    constexpr int PFC = GEOT_PF_C < PFMAX ? GEOT_PF_C : PFMAX;
+    if (sh.pf == GEOT_PF_C && ShapeOf<T, VECW, LPR, VPL, PFC>::max_blocks >= 1)
+      return launch_pf<T, VECW, LPR, VPL, RED, WM, PFC>(p, sh, stream);
+#endif
+  }
+  return launch_pf<T, VECW, LPR, VPL, RED, WM, 0>(p, sh, stream);
 }
 
 // sum kernels exist per weight mode; max / min / prod are built for the generic weight mode only

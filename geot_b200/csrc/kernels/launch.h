@@ -12,6 +12,7 @@ struct Shape {
   int vpl;        // vectors per lane: 1, 2 or 4 (only with lpr == 32)
   int col_tiles;  // ceil(W / (lpr*vpl*vecw)); grid.x = n_tiles * col_tiles, column tile is the slow index
   int wm;         // WM_NONE / WM_EDGE / WM_GENERIC (sum kernels; the other reduce ops are built WM_GENERIC only)
+  int pf;         // 0: gathered rows go straight to registers; > 0: cp.async shared-memory ring, pf sub-batches in flight
 };
 
 // ev0 / ev1 (optional): recorded on `stream` right before / after the main kernel (profiling hook)

@@ -129,16 +129,52 @@ template <> __device__ __forceinline__ float ld_stream_t<float>(const float *p, 
 #ifndef GEOT_MINB
 #define GEOT_MINB 2
 #endif
+#ifndef GEOT_RING_U
+#define GEOT_RING_U 0      // tuning builds: 16-byte pieces per lane per ring sub-batch (rows = GEOT_RING_U / VPL); 0 = built-in choice
+#endif
 
-template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
-__global__ void __launch_bounds__(kThreads, (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1)))
+// Shape constants shared by the kernel and its launcher.
+//   PF == 0: gathered rows go global -> registers (U loads in flight per group).
+//   PF  > 0: gathered rows are staged through a per-group shared-memory ring by cp.async (LDGSTS.128, L1
+//            bypassed): PF sub-batches of U rows are in flight while one is consumed, so the bytes in flight
+//            are bounded by shared memory (up to ~128 KB per SM) instead of by registers.  Every lane reads
+//            back only the 16-byte pieces it copied itself: cp.async.wait_group is the only synchronisation.
+template <typename T, int VECW, int LPR, int VPL, int PF>
+struct ShapeOf {
+  using A = typename AccOf<T>::type;
+  static constexpr int NG = kThreads / LPR;      // chunks (groups) per tile
+  static constexpr int CW = LPR * VPL * VECW;    // columns per CTA
+  // ring: 4 rows per sub-batch (2 for the widest rows) measured best on B200 (profiles/r01_ring_sweep.md)
+  static constexpr int RU = GEOT_RING_U > 0 ? (GEOT_RING_U / VPL > 0 ? GEOT_RING_U / VPL : 1) : (VPL >= 4 ? 2 : 4);
+  static constexpr int U0 = PF > 0 ? RU : ((VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0));
+  static constexpr int U = (LPR < U0) ? LPR : U0;   // rows per sub-batch
+  static constexpr int NS = PF + 1;              // ring stages
+  static constexpr size_t carry_bytes = ((2 * (size_t)NG * CW * sizeof(A) + (size_t)NG * (4 * 8 + 4)) + 127) & ~(size_t)127;
+  static constexpr size_t ring_bytes = PF > 0 ? (size_t)NG * NS * U * CW * sizeof(T) : 0;
+  static constexpr size_t smem_bytes = carry_bytes + ring_bytes;
+  static constexpr int max_blocks = (int)((227 * 1024) / (smem_bytes + 1024));
+  static constexpr int min_blocks_direct = (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1));
+  static constexpr int min_blocks = PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1));
+  static_assert(PF == 0 || PF * U <= LPR, "the prefetch distance must stay within one batch ahead");
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int VECW, int LPR, int VPL, int RED, int WM, int PF>
+__global__ void __launch_bounds__(kThreads, (ShapeOf<T, VECW, LPR, VPL, PF>::min_blocks))
 segment_reduce_kernel(const Params p) {
   using A = typename AccOf<T>::type;
   using VecT = Vec<T, VECW>;
-  constexpr int NG = kThreads / LPR;      // chunks per tile
-  constexpr int CW = LPR * VPL * VECW;    // columns per CTA
-  constexpr int U0 = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0);
-  constexpr int U = (LPR < U0) ? LPR : U0;   // row loads in flight per group
+  using SH = ShapeOf<T, VECW, LPR, VPL, PF>;
+  constexpr int NG = SH::NG;      // chunks per tile
+  constexpr int CW = SH::CW;      // columns per CTA
+  constexpr int U = SH::U;        // row loads in flight per group (PF == 0) / rows per ring sub-batch
+  constexpr int NS = SH::NS;
+  static_assert(PF == 0 || VECW * sizeof(T) == 16, "the cp.async ring moves 16-byte pieces");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A *s_head = reinterpret_cast<A *>(smem_raw);              // [NG][CW]
@@ -189,6 +225,14 @@ segment_reduce_kernel(const Params p) {
     lane_w[j] = (WM == WM_GENERIC && weight != nullptr) ? weight + (c / p.F) * p.ws_h : nullptr;
   }
   const int64_t row_bytes = W * (int64_t)sizeof(T);
+
+  // this group's ring: NS stages of U rows; lane piece j of row r at r*CW + (j*LPR + gl)*VECW
+  T *ring = nullptr;
+  uint32_t ring_s = 0;
+  if constexpr (PF > 0) {
+    ring = reinterpret_cast<T *>(smem_raw + SH::carry_bytes) + (size_t)g * (NS * U * CW) + gl * VECW;
+    ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  }
 
   A acc[VPL][VECW];    // the open run
 #pragma unroll
@@ -269,16 +313,41 @@ segment_reduce_kernel(const Params p) {
       if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + my_e, pol));
     };
 
-    int64_t my_dst, my_off;
-    A my_w;
+    // operands of the current batch (my_*) and of the next one (n_*); the one after that is loaded at the
+    // top of every iteration, so index / weight loads are two batches ahead of their first use
+    int64_t my_dst, my_off, n_dst = -2, n_off = 0;
+    A my_w, n_w = A(1);
     load_batch(e_begin, (int)min((int64_t)LPR, e_end - e_begin), my_dst, my_off, my_w);
+    if (e_begin + LPR < e_end) load_batch(e_begin + LPR, (int)min((int64_t)LPR, e_end - e_begin - LPR), n_dst, n_off, n_w);
+
+    // ring: copies sub-batch [kk, kk+U) of a batch (row offsets in `offs`, one per lane) into `stage`
+    auto ring_issue = [&](int64_t offs, int kk, int stage) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t off = __shfl_sync(gmask, offs, kk + u, LPR);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+          cp_async_16(ring_s + (uint32_t)(((stage * U + u) * CW + j * LPR * VECW) * sizeof(T)), lane_src[j] + off);
+      }
+    };
+    int stage = 0;              // ring stage of the sub-batch consumed next
+    if constexpr (PF > 0) {
+      // prologue: the first PF sub-batches of the chunk (only a full first batch uses the ring)
+      const bool full0 = (e_end - e_begin) >= LPR;
+#pragma unroll
+      for (int q = 0; q < PF; ++q) {
+        if (full0) ring_issue(my_off, q * U, q);
+        cp_async_commit();
+      }
+    }
 
     for (int64_t b = e_begin; b < e_end; b += LPR) {
       const int nb = (int)min((int64_t)LPR, e_end - b);
-      // issue the next batch's operand loads before touching this batch
-      int64_t n_dst = -2, n_off = 0;
-      A n_w = A(1);
-      if (b + LPR < e_end) load_batch(b + LPR, (int)min((int64_t)LPR, e_end - b - LPR), n_dst, n_off, n_w);
+      // issue the operand loads of the batch after the next before touching this one
+      int64_t nn_dst = -2, nn_off = 0;
+      A nn_w = A(1);
+      if (b + 2 * LPR < e_end) load_batch(b + 2 * LPR, (int)min((int64_t)LPR, e_end - b - 2 * LPR), nn_dst, nn_off, nn_w);
+      const bool next_full = (e_end - b) >= 2 * LPR;
 
       // segment heads of this batch as a bitmask (bit k: edge b+k starts a new dst row)
       int64_t left = __shfl_up_sync(gmask, my_dst, 1, LPR);
@@ -297,15 +366,38 @@ segment_reduce_kernel(const Params p) {
         for (int k0 = 0; k0 < LPR; k0 += U) {
           VecT v[U][VPL];
           A w[U][VPL];
+          if constexpr (PF > 0) {
+            // keep PF sub-batches in flight: issue the one PF ahead (this batch or the next), then wait for
+            // the oldest and read this lane's own pieces back
+            const int kk = k0 + PF * U;
+            int st = stage + PF;
+            if (st >= NS) st -= NS;
+            if (kk < LPR) ring_issue(my_off, kk, st);
+            else if (next_full) ring_issue(n_off, kk - LPR, st);
+            cp_async_commit();
+            cp_async_wait<PF>();
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int64_t off = __shfl_sync(gmask, my_off, k0 + u, LPR);
-            const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
+            for (int u = 0; u < U; ++u) {
+              const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
 #pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-              v[u][j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
-              w[u][j] = we;
-              if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
+              for (int j = 0; j < VPL; ++j) {
+                v[u][j] = *reinterpret_cast<const VecT *>(ring + ((stage * U + u) * CW + j * LPR * VECW));
+                w[u][j] = we;
+                if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
+              }
+            }
+            stage = (stage + 1 == NS) ? 0 : stage + 1;
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int64_t off = __shfl_sync(gmask, my_off, k0 + u, LPR);
+              const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
+#pragma unroll
+              for (int j = 0; j < VPL; ++j) {
+                v[u][j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
+                w[u][j] = we;
+                if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
+              }
             }
           }
           const unsigned sub = (bmask >> k0) & low_bits<U>();
@@ -346,6 +438,7 @@ segment_reduce_kernel(const Params p) {
         }
       }
       my_dst = n_dst; my_off = n_off; my_w = n_w;
+      n_dst = nn_dst; n_off = nn_off; n_w = nn_w;
     }
 
     // the run still open at the chunk end

@@ -81,24 +81,29 @@ def shard_graph(src_index: Optional[torch.Tensor], dst_index: torch.Tensor, weig
     return GraphShard(rank, world_size, list(row_bounds), list(edge_bounds), local_src, local_dst, local_w)
 
 
-def all_gather_rows(x_local: torch.Tensor, row_bounds: List[int], group=None) -> torch.Tensor:
+def all_gather_rows(x_local: torch.Tensor, row_bounds: List[int], group=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """All-gather ragged row shards into the full ``[N, ...]`` matrix (NCCL over NVLink on GPUs).
 
-    Shards are padded to the largest one so that a single ``all_gather_into_tensor`` moves the data
-    (one NCCL kernel at NVSwitch bandwidth) and then compacted in place."""
+    Edge-balanced shards own different numbers of rows.  On NCCL every rank's rows land directly in their
+    place in ``out`` (``all_gather`` with uneven outputs = one grouped set of broadcasts, no padding and no
+    compaction pass); equal shards take the single ``all_gather_into_tensor`` path.  Gloo (CPU tests) has no
+    uneven all-gather: shards are padded to the largest one and compacted."""
     world = dist.get_world_size(group)
     sizes = [row_bounds[g + 1] - row_bounds[g] for g in range(world)]
-    n_max = max(sizes)
     tail = list(x_local.shape[1:])
-    if all(s == n_max for s in sizes):
-        full = x_local.new_empty([n_max * world] + tail)
-        dist.all_gather_into_tensor(full, x_local.contiguous(), group=group)
+    x_local = x_local.contiguous()
+    full = out if out is not None else x_local.new_empty([row_bounds[-1]] + tail)
+    if all(s == sizes[0] for s in sizes):
+        dist.all_gather_into_tensor(full, x_local, group=group)
         return full
+    if x_local.is_cuda:
+        dist.all_gather([full[row_bounds[g]:row_bounds[g + 1]] for g in range(world)], x_local, group=group)
+        return full
+    n_max = max(sizes)
     pad = x_local.new_zeros([n_max] + tail)
     pad[: x_local.shape[0]] = x_local
     buf = x_local.new_empty([n_max * world] + tail)
     dist.all_gather_into_tensor(buf, pad, group=group)
-    full = x_local.new_empty([row_bounds[-1]] + tail)
     for g in range(world):
         full[row_bounds[g]:row_bounds[g + 1]] = buf[g * n_max: g * n_max + sizes[g]]
     return full

@@ -44,13 +44,5 @@ def format_preprocess(dst_index: torch.Tensor) -> Plan:
     return Plan(rowptr, e, s, nseg, maxdeg, bool(is_sorted), bool(has_gaps))
 
 
-def coo_to_csr(row: torch.Tensor, num_rows: int = None) -> torch.Tensor:
-    """CSR rowptr of a sorted COO row index (``geot::coo_to_csr``)."""
-    rp = format_preprocess(row).rowptr
-    if num_rows is not None and num_rows + 1 > rp.numel():
-        rp = torch.cat([rp, rp[-1:].expand(num_rows + 1 - rp.numel())])
-    return rp
-
-
 def clear_plan_cache() -> None:
     torch.ops.geot.clear_plan_cache()

@@ -32,11 +32,10 @@ def _setup_context(ctx, inputs, output):
 def _backward(ctx, grad):
     src_index, dst_index = ctx.saved_tensors
     grad = grad.contiguous()
-    # transposed edge list: sort by src (stable, keeps the dst order inside a src row)
-    _, perm = torch.sort(src_index, stable=True)
-    dst_index_bwd = src_index[perm]
-    src_index_bwd = dst_index[perm]
-    g = gather_scatter_impl(src_index_bwd, dst_index_bwd, grad)
+    # transposed edge list: sorted by src (stable, keeps the dst order inside a src row), cached per graph
+    from .transpose import transposed_edges
+    t = transposed_edges(src_index, dst_index)
+    g = gather_scatter_impl(t.src_index, t.dst_index, grad)
     if g.shape[0] < ctx.n_src:  # trailing src rows that no edge reads
         g = torch.cat([g, g.new_zeros(ctx.n_src - g.shape[0], g.shape[1])], 0)
     return None, None, g

@@ -151,6 +151,21 @@ GEOT_API int geot_b200_mh_spmm(const void *src, const int64_t *src_index, const 
                       int dtype, int reduce, int weight_layout, const geot_plan_t *plan,
                       void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* Replaces sddmm_coo_cuda (header_cuda.h:19-21; gather_weight_scatter_cuda.cu:41-62), the weight gradient
+ * of gather_weight_scatter (geot/gather_weight_scatter.py:47):
+ *     out[e] = < mat1[row_index[e], :], mat2[col_index[e], :] >        mat1 [N1,F], mat2 [N2,F], out [E]
+ * all of `dtype` (the reference is fp32 + int32 indices only); bf16/fp16 accumulate in fp32.  No scratch,
+ * no sortedness requirement; a sorted row_index lets the kernel keep the mat1 row in registers. */
+GEOT_API int geot_b200_sddmm_coo(const void *mat1, const int64_t *row_index, const void *mat2,
+                        const int64_t *col_index, void *out, int64_t E, int64_t F, int dtype,
+                        cudaStream_t stream);
+
+/* CSR row pointer -> sorted COO row index (the inverse of geot::coo_to_csr): row_index[e] = r for
+ * rowptr[r] <= e < rowptr[r+1].  rowptr has S+1 entries of 32 or 64 bits (rowptr_bits).  Lets the CSR entry
+ * point csr_gws (csrc/csr_gws.cpp:24-35, csr_gws_cuda.cu) run on the same kernels. */
+GEOT_API int geot_b200_csr_to_coo(const void *rowptr, int rowptr_bits, int64_t S, int64_t E, int64_t *row_index,
+                         cudaStream_t stream);
+
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------------- */
 
 /* Same operation with every operand in HOST memory (pinned memory makes the copies asynchronous).

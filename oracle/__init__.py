@@ -155,6 +155,41 @@ def mh_spmm(src_index, dst_index, weight, src, reduce="sum", **kw):
     raise RuntimeError("Invalid weight size")
 
 
+def sddmm_coo(src_index, dst_index, mat_1, mat_2):
+    """out[e] = <mat_1[dst_index[e]], mat_2[src_index[e]]> (geot::sddmm_coo_impl argument order,
+    csrc/gather_weight_scatter.cpp:36-44); low precision upcast to fp32, f64 accumulate, rounded once."""
+    out_dtype = mat_1.dtype
+    comp = torch.float64 if out_dtype == torch.float64 else torch.float32
+    a = mat_1.detach().cpu().to(comp).contiguous()
+    b = mat_2.detach().cpu().to(comp).contiguous()
+    row = dst_index.detach().cpu().long().contiguous()
+    col = src_index.detach().cpu().long().contiguous()
+    E, F = row.numel(), a.shape[1]
+    out = torch.empty(E, dtype=comp)
+    fn = lib().geot_oracle_sddmm_f64 if comp == torch.float64 else lib().geot_oracle_sddmm_f32
+    fn(_p(a), _p(row), _p(b), _p(col), _p(out), ctypes.c_int64(E), ctypes.c_int64(F))
+    return out.to(out_dtype)
+
+
+def csr_gws(csrptr, csrind, weight, src):
+    """geot.csr_gws (csrc/csr_gws.cpp:24-35): fp32, output rows = csrptr.numel() (nrow + 1, last row 0)."""
+    ptr = csrptr.detach().cpu().long().contiguous()
+    ind = csrind.detach().cpu().long().contiguous()
+    val = weight.detach().cpu().float().contiguous()
+    x = src.detach().cpu().float().contiguous()
+    nrow, F = ptr.numel() - 1, x.shape[1]
+    out = torch.empty(nrow + 1, F, dtype=torch.float32)
+    lib().geot_oracle_csr_gws_f32(_p(ptr), _p(ind), _p(val), _p(x), _p(out), ctypes.c_int64(nrow), ctypes.c_int64(F))
+    return out.to(src.dtype)
+
+
+def csr_to_coo(csrptr):
+    ptr = csrptr.detach().cpu().long().contiguous()
+    row = torch.empty(int(ptr[-1]), dtype=torch.int64)
+    lib().geot_oracle_csr_to_coo(_p(ptr), ctypes.c_int64(ptr.numel() - 1), _p(row))
+    return row
+
+
 # ---- torch formulas used by the reference's own tests -----------------------------------------
 
 def torch_index_scatter(index, src, reduce="sum", S=None):

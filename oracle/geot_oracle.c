@@ -182,3 +182,52 @@ int geot_oracle_reduce_f32_mt(const float *src, const int64_t *src_index, const 
   free(rowptr);
   return nthreads;
 }
+
+/* ---- SDDMM on a COO edge list ---------------------------------------------------------------- */
+
+/* out[e] = < mat1[row[e], :], mat2[col[e], :] >.  Follows the reference kernel's definition
+ * (csrc/cuda/sddmm_coo_kernel.cuh:44-71, the scalar tail path: offset1 = S_cooRowInd[eid]*D_kcols,
+ * offset2 = S_cooColInd[eid]*D_kcols, multi += D1[offset1+c]*D2[offset2+c]) with row = dst_index and
+ * col = src_index as the launcher binds them (csrc/cuda/gather_weight_scatter_cuda.cu:46-50).
+ * Accumulates in double: the tight-tolerance oracle. */
+void geot_oracle_sddmm_f32(const float *mat1, const int64_t *row, const float *mat2, const int64_t *col,
+                           float *out, int64_t E, int64_t F) {
+  for (int64_t e = 0; e < E; ++e) {
+    const float *x = mat1 + row[e] * F, *y = mat2 + col[e] * F;
+    double s = 0.0;
+    for (int64_t c = 0; c < F; ++c) s += (double)x[c] * (double)y[c];
+    out[e] = (float)s;
+  }
+}
+void geot_oracle_sddmm_f64(const double *mat1, const int64_t *row, const double *mat2, const int64_t *col,
+                           double *out, int64_t E, int64_t F) {
+  for (int64_t e = 0; e < E; ++e) {
+    const double *x = mat1 + row[e] * F, *y = mat2 + col[e] * F;
+    double s = 0.0;
+    for (int64_t c = 0; c < F; ++c) s += x[c] * y[c];
+    out[e] = s;
+  }
+}
+
+/* ---- CSR SpMM (csr_gws) ------------------------------------------------------------------------ */
+
+/* out[r, :] = sum_{e in [rowptr[r], rowptr[r+1])} val[e] * src[colind[e], :] for r < nrow, and one extra
+ * zero row: the reference allocates indptr.size(0) = nrow + 1 output rows (csrc/csr_gws.cpp:29-31) and its
+ * kernel writes rows < nrow only (csr_gws_kernel.cuh:13-187).  Sequential edge order; f64 accumulate. */
+void geot_oracle_csr_gws_f32(const int64_t *rowptr, const int64_t *colind, const float *val, const float *src,
+                             float *out, int64_t nrow, int64_t F) {
+  for (int64_t r = 0; r <= nrow; ++r) {
+    for (int64_t c = 0; c < F; ++c) {
+      double s = 0.0;
+      if (r < nrow)
+        for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) s += (double)((float)(val[e] * src[colind[e] * F + c]));
+      out[r * F + c] = (float)s;
+    }
+  }
+}
+
+/* row index of every nonzero of a CSR matrix (the inverse of geot_oracle_rowptr) */
+void geot_oracle_csr_to_coo(const int64_t *rowptr, int64_t nrow, int64_t *row) {
+  for (int64_t r = 0; r < nrow; ++r)
+    for (int64_t e = rowptr[r]; e < rowptr[r + 1]; ++e) row[e] = r;
+}

@@ -242,7 +242,7 @@ def test_format_preprocess_bit_exact(E, N, gaps):
     assert (plan.num_edges, plan.num_rows, plan.num_segments) == (E, S, rows.numel())
     assert plan.max_degree == int((offs[1:] - offs[:-1]).max())
     assert plan.is_sorted and plan.has_gaps == (rows.numel() < S)
-    assert torch.equal(geot_b200.coo_to_csr(di.to(DEV)).cpu(), oracle.rowptr(di, S))
+    assert torch.equal(geot_b200.coo_to_csr(di.to(DEV)).cpu().long(), oracle.rowptr(di, S))   # int32 like the reference
     # the ABI-level plan agrees and the shard rule matches the host restatement
     p2 = abi.DevicePlan(di.to(DEV))
     assert torch.equal(p2.rowptr.cpu(), plan.rowptr.cpu())

@@ -36,19 +36,21 @@ cudaError_t launch_pf(const Params &p, const Shape &sh, cudaStream_t stream) {
 #endif
 template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
 cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
-  if constexpr (RED == RED_SUM && WM != WM_GENERIC && VECW * sizeof(T) == 16 && LPR >= 8) {
+  if constexpr (RED == RED_SUM && VECW * sizeof(T) == 16 && LPR >= 8) {
     constexpr int U = ShapeOf<T, VECW, LPR, VPL, 1>::U;   // ring sub-batch
     constexpr int PFMAX = LPR / U;
-    constexpr int PFA = GEOT_PF_A < PFMAX ? GEOT_PF_A : PFMAX;
+    // a list entry is depth (+ kTmaFlag for the TMA-filled ring); the depth is clamped to what the batch allows
+#define GEOT_CLAMP_PF(X) ((((X) & (kTmaFlag - 1)) < PFMAX ? ((X) & (kTmaFlag - 1)) : PFMAX) | ((X) & kTmaFlag))
+    constexpr int PFA = GEOT_CLAMP_PF(GEOT_PF_A);
     if (sh.pf == GEOT_PF_A && ShapeOf<T, VECW, LPR, VPL, PFA>::max_blocks >= 1)
       return launch_pf<T, VECW, LPR, VPL, RED, WM, PFA>(p, sh, stream);
 #ifdef GEOT_PF_B
-    constexpr int PFB = GEOT_PF_B < PFMAX ? GEOT_PF_B : PFMAX;
+    constexpr int PFB = GEOT_CLAMP_PF(GEOT_PF_B);
     if (sh.pf == GEOT_PF_B && ShapeOf<T, VECW, LPR, VPL, PFB>::max_blocks >= 1)
       return launch_pf<T, VECW, LPR, VPL, RED, WM, PFB>(p, sh, stream);
 #endif
 #ifdef GEOT_PF_C
-    constexpr int PFC = GEOT_PF_C < PFMAX ? GEOT_PF_C : PFMAX;
+    constexpr int PFC = GEOT_CLAMP_PF(GEOT_PF_C);
     if (sh.pf == GEOT_PF_C && ShapeOf<T, VECW, LPR, VPL, PFC>::max_blocks >= 1)
       return launch_pf<T, VECW, LPR, VPL, RED, WM, PFC>(p, sh, stream);
 #endif

@@ -139,9 +139,15 @@ template <> __device__ __forceinline__ float ld_stream_t<float>(const float *p, 
 //            bypassed): PF sub-batches of U rows are in flight while one is consumed, so the bytes in flight
 //            are bounded by shared memory (up to ~128 KB per SM) instead of by registers.  Every lane reads
 //            back only the 16-byte pieces it copied itself: cp.async.wait_group is the only synchronisation.
-template <typename T, int VECW, int LPR, int VPL, int PF>
+//   PF >= 16: the same ring filled by TMA bulk copies (cp.async.bulk.shared.global, UBLKCP) of depth PF - 16:
+//            lane k issues ONE copy for the whole row of edge k (no offset shuffles, no per-lane LDGSTS, the
+//            L1/LSU path is not involved); completion is an mbarrier transaction count per ring stage.
+constexpr int kTmaFlag = 16;
+template <typename T, int VECW, int LPR, int VPL, int PF_>
 struct ShapeOf {
   using A = typename AccOf<T>::type;
+  static constexpr bool TMA = PF_ >= kTmaFlag;
+  static constexpr int PF = PF_ & (kTmaFlag - 1);   // ring depth
   static constexpr int NG = kThreads / LPR;      // chunks (groups) per tile
   static constexpr int CW = LPR * VPL * VECW;    // columns per CTA
   // ring: 4 rows per sub-batch (2 for the widest rows) measured best on B200 (profiles/r01_ring_sweep.md)
@@ -151,7 +157,8 @@ struct ShapeOf {
   static constexpr int NS = PF + 1;              // ring stages
   static constexpr size_t carry_bytes = ((2 * (size_t)NG * CW * sizeof(A) + (size_t)NG * (4 * 8 + 4)) + 127) & ~(size_t)127;
   static constexpr size_t ring_bytes = PF > 0 ? (size_t)NG * NS * U * CW * sizeof(T) : 0;
-  static constexpr size_t smem_bytes = carry_bytes + ring_bytes;
+  static constexpr size_t bar_bytes = TMA ? (((size_t)NG * NS * 8 + 127) & ~(size_t)127) : 0;   // one mbarrier per (group, stage)
+  static constexpr size_t smem_bytes = carry_bytes + ring_bytes + bar_bytes;
   static constexpr int max_blocks = (int)((227 * 1024) / (smem_bytes + 1024));
   static constexpr int min_blocks_direct = (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1));
   static constexpr int min_blocks = PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1));
@@ -164,17 +171,43 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *gptr
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <typename T, int VECW, int LPR, int VPL, int RED, int WM, int PF>
-__global__ void __launch_bounds__(kThreads, (ShapeOf<T, VECW, LPR, VPL, PF>::min_blocks))
+// mbarrier + TMA bulk copy (1-D): global -> this CTA's shared memory, completion counted in bytes on the barrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *gptr, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(gptr), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <typename T, int VECW, int LPR, int VPL, int RED, int WM, int PF_>
+__global__ void __launch_bounds__(kThreads, (ShapeOf<T, VECW, LPR, VPL, PF_>::min_blocks))
 segment_reduce_kernel(const Params p) {
   using A = typename AccOf<T>::type;
   using VecT = Vec<T, VECW>;
-  using SH = ShapeOf<T, VECW, LPR, VPL, PF>;
+  using SH = ShapeOf<T, VECW, LPR, VPL, PF_>;
+  constexpr int PF = SH::PF;
+  constexpr bool TMA = SH::TMA;
   constexpr int NG = SH::NG;      // chunks per tile
   constexpr int CW = SH::CW;      // columns per CTA
   constexpr int U = SH::U;        // row loads in flight per group (PF == 0) / rows per ring sub-batch
   constexpr int NS = SH::NS;
-  static_assert(PF == 0 || VECW * sizeof(T) == 16, "the cp.async ring moves 16-byte pieces");
+  static_assert(PF == 0 || VECW * sizeof(T) == 16, "the ring moves 16-byte pieces");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A *s_head = reinterpret_cast<A *>(smem_raw);              // [NG][CW]
@@ -229,9 +262,20 @@ segment_reduce_kernel(const Params p) {
   // this group's ring: NS stages of U rows; lane piece j of row r at r*CW + (j*LPR + gl)*VECW
   T *ring = nullptr;
   uint32_t ring_s = 0;
+  uint32_t bars_s = 0;          // TMA: this group's NS mbarriers
   if constexpr (PF > 0) {
     ring = reinterpret_cast<T *>(smem_raw + SH::carry_bytes) + (size_t)g * (NS * U * CW) + gl * VECW;
     ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+  }
+  if constexpr (TMA) {
+    bars_s = (uint32_t)__cvta_generic_to_shared(smem_raw + SH::carry_bytes + SH::ring_bytes) + (uint32_t)(g * NS * 8);
+    if (gl == 0) {
+#pragma unroll
+      for (int q = 0; q < NS; ++q) mbar_init(bars_s + q * 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp(gmask);
   }
 
   A acc[VPL][VECW];    // the open run
@@ -321,13 +365,28 @@ segment_reduce_kernel(const Params p) {
     if (e_begin + LPR < e_end) load_batch(e_begin + LPR, (int)min((int64_t)LPR, e_end - e_begin - LPR), n_dst, n_off, n_w);
 
     // ring: copies sub-batch [kk, kk+U) of a batch (row offsets in `offs`, one per lane) into `stage`
+    // bytes of one row inside this CTA's column slab (TMA copies exactly the slab)
+    const uint32_t slab_bytes = (uint32_t)(min((int64_t)CW, W - col0) * (int64_t)sizeof(T));
+    const char *slab_src = reinterpret_cast<const char *>(src + col0);
+    uint32_t n_consumed = 0;    // TMA: sub-batches consumed so far (stage = n % NS, parity = (n / NS) & 1)
     auto ring_issue = [&](int64_t offs, int kk, int stage) {
+      if constexpr (TMA) {
+        // lane kk+u copies the row of edge kk+u (its own offset register) into slot (stage, u)
+        const uint32_t bar = bars_s + stage * 8;
+        if (gl == 0) mbar_expect_tx(bar, U * slab_bytes);
+        __syncwarp(gmask);          // every lane is done reading the slot's previous occupant; expect precedes the copies
+        const int u = gl - kk;
+        if (u >= 0 && u < U)
+          tma_load_1d(ring_s - (uint32_t)(gl * VECW * sizeof(T)) + (uint32_t)((stage * U + u) * CW * sizeof(T)), slab_src + offs,
+                      slab_bytes, bar);
+      } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t off = __shfl_sync(gmask, offs, kk + u, LPR);
+        for (int u = 0; u < U; ++u) {
+          const int64_t off = __shfl_sync(gmask, offs, kk + u, LPR);
 #pragma unroll
-        for (int j = 0; j < VPL; ++j)
-          cp_async_16(ring_s + (uint32_t)(((stage * U + u) * CW + j * LPR * VECW) * sizeof(T)), lane_src[j] + off);
+          for (int j = 0; j < VPL; ++j)
+            cp_async_16(ring_s + (uint32_t)(((stage * U + u) * CW + j * LPR * VECW) * sizeof(T)), lane_src[j] + off);
+        }
       }
     };
     int stage = 0;              // ring stage of the sub-batch consumed next
@@ -337,7 +396,7 @@ segment_reduce_kernel(const Params p) {
 #pragma unroll
       for (int q = 0; q < PF; ++q) {
         if (full0) ring_issue(my_off, q * U, q);
-        cp_async_commit();
+        if constexpr (!TMA) cp_async_commit();
       }
     }
 
@@ -374,8 +433,13 @@ segment_reduce_kernel(const Params p) {
             if (st >= NS) st -= NS;
             if (kk < LPR) ring_issue(my_off, kk, st);
             else if (next_full) ring_issue(n_off, kk - LPR, st);
-            cp_async_commit();
-            cp_async_wait<PF>();
+            if constexpr (TMA) {
+              mbar_wait(bars_s + stage * 8, (n_consumed / NS) & 1u);
+              ++n_consumed;
+            } else {
+              cp_async_commit();
+              cp_async_wait<PF>();
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);

@@ -13,6 +13,16 @@ w = wk["w"]
 layout = abi.W_NONE if w is None else (abi.W_EDGE if w.dim() == 1 else abi.W_EDGE_HEAD)
 plan = abi.DevicePlan(wk["di"], S)
 out = torch.empty([S] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device="cuda")
+# reference result: the register path (GEOT_B200_RING=0) of the same library
+_ring = os.environ.get("GEOT_B200_RING")
+os.environ["GEOT_B200_RING"] = "0"
+_ws = abi.Workspace(E, F * H, wk["dtype"], "cuda")
+ref = abi.segment_reduce(wk["x"], wk["si"], wk["di"], w, "sum", S=S, H=H, weight_layout=layout, plan=plan, workspace=_ws).clone()
+del _ws
+if _ring is None:
+    del os.environ["GEOT_B200_RING"]
+else:
+    os.environ["GEOT_B200_RING"] = _ring
 for c in chunks:
     os.environ["GEOT_B200_CHUNK"] = str(c)
     ws = abi.Workspace(E, F * H, wk["dtype"], "cuda")
@@ -26,6 +36,7 @@ for c in chunks:
     e1.record(); torch.cuda.synchronize()
     km = abi.profile_read(10); abi.profile_enable(0)
     ms = e0.elapsed_time(e1) / 10
-    print("%s lib=%s chunk=%d: step %.3f ms (%.0f GB/s logical, %.2f Gedge/s)  main kernel %.3f ms  fixup+gaps %.3f ms" % (
+    err = float(((out.float() - ref.float()).abs() / ref.float().abs().clamp_min(1e-20)).max())
+    print("%s lib=%s chunk=%d: step %.3f ms (%.0f GB/s logical, %.2f Gedge/s)  main kernel %.3f ms  fixup+gaps %.3f ms  maxrel_vs_ring0 %.1e" % (
         name, os.path.basename(os.environ.get("GEOT_B200_LIB", "default")), c, ms, wk["bytes_logical"] / ms / 1e6, E / ms / 1e6,
-        sum(km) / len(km), ms - sum(km) / len(km)), flush=True)
+        sum(km) / len(km), ms - sum(km) / len(km), err), flush=True)

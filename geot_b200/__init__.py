@@ -39,7 +39,8 @@ from .gather_weight_scatter import sddmm_coo_impl  # noqa: E402
 from .csr_gws import csr_gws, coo_to_csr  # noqa: E402
 from .format_preprocess import format_preprocess, Plan, clear_plan_cache  # noqa: E402
 from . import fake as _fake  # noqa: E402,F401  (register_fake for the C++-registered operators)
+from .match_replace import pattern_transform  # noqa: E402
 from . import dist  # noqa: E402
 
 __all__ = ["index_scatter", "gather_scatter", "gather_weight_scatter", "mh_spmm", "mh_spmm_transposed", "csr_gws",
-           "coo_to_csr", "sddmm_coo_impl", "format_preprocess", "Plan", "clear_plan_cache", "dist"]
+           "coo_to_csr", "sddmm_coo_impl", "pattern_transform", "format_preprocess", "Plan", "clear_plan_cache", "dist"]

@@ -198,3 +198,23 @@ def test_against_reference_cuda_kernels_next():
         ref = torch.ops.geot_ref.csr_gws_impl(rowptr, si, w, x2)
         assert ours.shape == ref.shape
         assert ((ours - ref).abs() <= 2e-5 * ref.abs().clamp_min(1e-30)).all(), (E, N, F)
+
+
+def test_pattern_transform_numerics():
+    """The rewritten program computes what the original torch program computes (test/compile/test_gcn.py prints this diff)."""
+    from tests.test_next_host import _mp_models
+    GCNLayer, MultiHead, _ = _mp_models()
+    g = torch.Generator().manual_seed(2)
+    N, E = 300, 5000
+    row = torch.randint(0, N, (E,), generator=g)
+    col = torch.randint(0, N - 7, (E,), generator=g).sort().values        # the last 7 nodes are isolated
+    ei = torch.stack([row, col]).to(DEV)
+    x, w = torch.rand(N, 8, generator=g).to(DEV), torch.rand(E, generator=g).to(DEV)
+    model = GCNLayer().to(DEV)
+    ep = geot_b200.pattern_transform(model, (x, ei, w))
+    out, ref = ep.module()(x, ei, w), model(x, ei, w)
+    assert out.shape == ref.shape == (N, 16)
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5)
+    xh, wh = torch.rand(N, 4, 8, generator=g).to(DEV), torch.rand(E, 4, generator=g).to(DEV)
+    ep = geot_b200.pattern_transform(MultiHead(), (xh, ei[0], ei[1], wh))
+    assert torch.allclose(ep.module()(xh, ei[0], ei[1], wh), MultiHead()(xh, ei[0], ei[1], wh), rtol=1e-4, atol=1e-5)

@@ -106,3 +106,49 @@ def test_gcn_norm_and_self_loops_match_the_reference_formulas():
     m = gnn.GCN(8, 16, 3)
     assert [c.lin.weight.shape for c in m.convs] == [(16, 8), (16, 16), (16, 16)]
     assert len(gnn.GraphSAGE(8, 16, 3, 4).convs) == 3
+
+
+def _mp_models():
+    class GCNLayer(torch.nn.Module):          # PyG-style message passing spelled with aten ops
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(8, 16, bias=False)
+
+        def forward(self, x, edge_index, w):
+            row, col = edge_index[0], edge_index[1]
+            h = self.lin(x)
+            m = w.view(-1, 1) * h.index_select(0, row)
+            out = m.new_zeros((x.shape[0], 16)).index_add(0, col, m)
+            agg = h.new_zeros((x.shape[0], 16)).index_add(0, col, h.index_select(0, row))
+            return torch.relu(out) + agg
+
+    class MultiHead(torch.nn.Module):
+        def forward(self, x, row, col, w):
+            return torch.zeros_like(x).index_add(0, col, w.unsqueeze(-1) * x.index_select(0, row))
+
+    class NotAMatch(torch.nn.Module):           # accumulates into a non-zero base: must be left alone
+        def forward(self, x, row, col):
+            return x.index_add(0, col, x.index_select(0, row))
+
+    return GCNLayer, MultiHead, NotAMatch
+
+
+def test_pattern_transform_rewrites_message_passing_chains():
+    """geot/match_replace/match_replace.py:8-32: index_select -> (mul) -> index_add => geot operators."""
+    GCNLayer, MultiHead, NotAMatch = _mp_models()
+    g = torch.Generator().manual_seed(1)
+    N, E = 20, 100
+    ei = torch.stack([torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g).sort().values])
+    ep = geot_b200.pattern_transform(GCNLayer(), (torch.rand(N, 8), ei, torch.rand(E)))
+    targets = [str(n.target) for n in ep.graph_module.graph.nodes if n.op == "call_function"]
+    assert "geot.gather_weight_scatter.default" in targets and "geot.gather_scatter.default" in targets
+    assert not any("index_add" in t or "index_select" in t or "new_zeros" in t for t in targets)
+    assert targets.count("geot.pad_rows.default") == 2
+    ep = geot_b200.pattern_transform(MultiHead(), (torch.rand(N, 4, 8), ei[0], ei[1], torch.rand(E, 4)))
+    targets = [str(n.target) for n in ep.graph_module.graph.nodes if n.op == "call_function"]
+    assert "geot.mh_spmm.default" in targets and not any("index_add" in t for t in targets)
+    ep = geot_b200.pattern_transform(NotAMatch(), (torch.rand(N, 8), ei[0], ei[1]))
+    targets = [str(n.target) for n in ep.graph_module.graph.nodes if n.op == "call_function"]
+    assert any("index_add" in t for t in targets) and not any("geot" in t for t in targets)
+    x = torch.rand(3, 4)
+    assert torch.equal(torch.ops.geot.pad_rows(x, 5)[:3], x) and torch.ops.geot.pad_rows(x, 5)[3:].abs().sum() == 0

@@ -72,10 +72,12 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok)
   c.shape.vpl = vpl;
   c.shape.col_tiles = (int)((nvec + (int64_t)lpr * vpl - 1) / ((int64_t)lpr * vpl));
   c.shape.wm = 0;
-  // cp.async ring depth (sub-batches in flight per group) for the kernels that have one (sum, 16-byte vectors,
-  // rows of >= 8 vectors): 3 for 256-byte rows, 2 otherwise -- profiles/r01_ring_sweep.md.  GEOT_B200_RING=0
-  // selects the register path, another value a depth a tuning build carries.
-  c.shape.pf = env_int("GEOT_B200_RING", (vecw > 1 && lpr >= 8) ? (lpr == 16 ? 3 : 2) : 0);
+  // gathered rows through the cp.async shared-memory ring for the kernels that have one (sum, 16-byte vectors, rows
+  // of >= 8 vectors).  Default: the lean ring, depth 3 (4 stages of 2 KB per warp = 6 KB in flight per warp) --
+  // profiles/r01c_*; the launcher falls back to the first-generation ring (depth 3 for 256-byte rows, 2 otherwise,
+  // profiles/r01_ring_sweep.md) where the lean ring does not apply.  GEOT_B200_RING=0 selects the register path,
+  // 2 / 3 the first-generation ring, 32 + depth a lean depth.
+  c.shape.pf = env_int("GEOT_B200_RING", (vecw > 1 && lpr >= 8) ? (geot::kLeanFlag | 3) : 0);
   const int ng = geot::kThreads / lpr;
   // Edge-count partition: every group owns `chunk` consecutive edges.  Longer chunks amortise the
   // per-chunk carry handling; shorter ones keep small inputs spread over all 148 SMs.

@@ -28,30 +28,58 @@ cudaError_t launch_pf(const Params &p, const Shape &sh, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// Ring depths built: GEOT_PF_A / _B / _C (production: 2 and 3, the depths abi.cu selects; tuning builds override).
-// The ring needs 16-byte pieces, a sub-batch that fits PF times into a batch, and serves the sum kernels.
+// Ring variants built.  Production: the lean ring (kLeanFlag + depth; depths GEOT_LEAN_A / _B, clamped to what the
+// batch allows) for the sum kernels with fp32 accumulators and at most one weight per edge, and the first-generation
+// ring (GEOT_PF_A / _B = depths 2 and 3) for what the lean ring does not serve (fp64, per-head weights) and as the
+// A/B reference (GEOT_B200_RING=2).  Tuning builds override the lists; 16 + depth selects the TMA-filled ring.
 #ifndef GEOT_PF_A
 #define GEOT_PF_A 2
 #define GEOT_PF_B 3
 #endif
+#ifndef GEOT_LEAN_A
+#define GEOT_LEAN_A 3
+#define GEOT_LEAN_B 7
+#endif
+// largest lean depth d <= want with (d + 1) | SB
+constexpr int lean_depth(int want, int sb) {
+  int d = want < sb ? want : sb - 1;
+  while (d > 0 && sb % (d + 1) != 0) --d;
+  return d;
+}
 template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
 cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
   if constexpr (RED == RED_SUM && VECW * sizeof(T) == 16 && LPR >= 8) {
+    int pf = sh.pf;
+    if (pf & kLeanFlag) {
+      if constexpr (WM != WM_GENERIC && sizeof(typename AccOf<T>::type) == 4) {
+        if (p.chunk_edges % LPR == 0) {
+          constexpr int SB = ShapeOf<T, VECW, LPR, VPL, kLeanFlag | 1>::SB;
+          constexpr int DA = lean_depth(GEOT_LEAN_A, SB), DB = lean_depth(GEOT_LEAN_B, SB);
+          static_assert(DA >= 1 && DB >= 1, "a batch has at least two sub-batches");
+          const int want = pf & (kTmaFlag - 1);
+          if (want > DA && DB != DA && ShapeOf<T, VECW, LPR, VPL, kLeanFlag | DB>::max_blocks >= 1)
+            return launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DB>(p, sh, stream);
+          if (ShapeOf<T, VECW, LPR, VPL, kLeanFlag | DA>::max_blocks >= 1)
+            return launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DA>(p, sh, stream);
+        }
+      }
+      pf = (LPR == 16) ? GEOT_PF_B : GEOT_PF_A;   // not served by the lean ring: first-generation ring
+    }
     constexpr int U = ShapeOf<T, VECW, LPR, VPL, 1>::U;   // ring sub-batch
     constexpr int PFMAX = LPR / U;
     // a list entry is depth (+ kTmaFlag for the TMA-filled ring); the depth is clamped to what the batch allows
 #define GEOT_CLAMP_PF(X) ((((X) & (kTmaFlag - 1)) < PFMAX ? ((X) & (kTmaFlag - 1)) : PFMAX) | ((X) & kTmaFlag))
     constexpr int PFA = GEOT_CLAMP_PF(GEOT_PF_A);
-    if (sh.pf == GEOT_PF_A && ShapeOf<T, VECW, LPR, VPL, PFA>::max_blocks >= 1)
+    if (pf == GEOT_PF_A && ShapeOf<T, VECW, LPR, VPL, PFA>::max_blocks >= 1)
       return launch_pf<T, VECW, LPR, VPL, RED, WM, PFA>(p, sh, stream);
 #ifdef GEOT_PF_B
     constexpr int PFB = GEOT_CLAMP_PF(GEOT_PF_B);
-    if (sh.pf == GEOT_PF_B && ShapeOf<T, VECW, LPR, VPL, PFB>::max_blocks >= 1)
+    if (pf == GEOT_PF_B && ShapeOf<T, VECW, LPR, VPL, PFB>::max_blocks >= 1)
       return launch_pf<T, VECW, LPR, VPL, RED, WM, PFB>(p, sh, stream);
 #endif
 #ifdef GEOT_PF_C
     constexpr int PFC = GEOT_CLAMP_PF(GEOT_PF_C);
-    if (sh.pf == GEOT_PF_C && ShapeOf<T, VECW, LPR, VPL, PFC>::max_blocks >= 1)
+    if (pf == GEOT_PF_C && ShapeOf<T, VECW, LPR, VPL, PFC>::max_blocks >= 1)
       return launch_pf<T, VECW, LPR, VPL, RED, WM, PFC>(p, sh, stream);
 #endif
   }

@@ -143,30 +143,55 @@ template <> __device__ __forceinline__ float ld_stream_t<float>(const float *p, 
 //            lane k issues ONE copy for the whole row of edge k (no offset shuffles, no per-lane LDGSTS, the
 //            L1/LSU path is not involved); completion is an mbarrier transaction count per ring stage.
 constexpr int kTmaFlag = 16;
+//   PF & 32 (kLeanFlag): the LEAN ring -- the same cp.async ring with the per-edge bookkeeping moved out of the
+//            instruction stream.  The batch's src row ids (32 bit: a ring row is >= 128 bytes, so any valid row id
+//            of a 180 GB device fits) and weights are parked in a small per-group shared-memory buffer and come
+//            back U at a time with one broadcast LDS.128 each, instead of 3 SHFL + a 64-bit add per edge; the ring
+//            has NS = depth + 1 stages with NS | (LPR / U), so every stage address is an immediate of the unrolled
+//            batch; the run length is a difference of edge positions instead of a per-edge counter.  About 10 warp
+//            instructions per 512-byte row instead of 32 (profiles/r01c_*).  sum kernels with fp32 accumulators,
+//            no per-head weights, chunks that are whole batches.
+constexpr int kLeanFlag = 32;
 template <typename T, int VECW, int LPR, int VPL, int PF_>
 struct ShapeOf {
   using A = typename AccOf<T>::type;
-  static constexpr bool TMA = PF_ >= kTmaFlag;
+  static constexpr bool TMA = (PF_ & kTmaFlag) != 0;
+  static constexpr bool LEAN = (PF_ & kLeanFlag) != 0;
   static constexpr int PF = PF_ & (kTmaFlag - 1);   // ring depth
   static constexpr int NG = kThreads / LPR;      // chunks (groups) per tile
   static constexpr int CW = LPR * VPL * VECW;    // columns per CTA
   // ring: 4 rows per sub-batch (2 for the widest rows) measured best on B200 (profiles/r01_ring_sweep.md)
   static constexpr int RU = GEOT_RING_U > 0 ? (GEOT_RING_U / VPL > 0 ? GEOT_RING_U / VPL : 1) : (VPL >= 4 ? 2 : 4);
-  static constexpr int U0 = PF > 0 ? RU : ((VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0));
+  // lean ring: 2 KB of rows per warp and stage, at least 4 sub-batches per batch
+  static constexpr int LU = (VPL >= 4) ? 1 : (VPL == 2 ? 2 : (LPR >= 16 ? 4 : (LPR >= 8 ? 2 : 1)));
+  static constexpr int U0 = LEAN ? LU : (PF > 0 ? RU : ((VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0)));
   static constexpr int U = (LPR < U0) ? LPR : U0;   // rows per sub-batch
   static constexpr int NS = PF + 1;              // ring stages
-  static constexpr size_t carry_bytes = ((2 * (size_t)NG * CW * sizeof(A) + (size_t)NG * (4 * 8 + 4)) + 127) & ~(size_t)127;
+  static constexpr int SB = LPR / U;             // sub-batches per batch
+  // carries: head (and tail, unless it is parked in the group's own drained ring) + per-chunk scalars
+  static constexpr size_t tail_off = (size_t)NG * CW * sizeof(A);
+  static constexpr size_t scalars_off = (LEAN ? 1 : 2) * (size_t)NG * CW * sizeof(A);
+  static constexpr size_t carry_bytes = ((scalars_off + (size_t)NG * (4 * 8 + 4)) + 127) & ~(size_t)127;
+  // lean: per group two operand buffers of LPR src row ids + LPR weights
+  static constexpr size_t ops_bytes = LEAN ? (size_t)NG * 4 * LPR * 4 : 0;
+  static constexpr size_t ring_off = carry_bytes + ops_bytes;
   static constexpr size_t ring_bytes = PF > 0 ? (size_t)NG * NS * U * CW * sizeof(T) : 0;
   static constexpr size_t bar_bytes = TMA ? (((size_t)NG * NS * 8 + 127) & ~(size_t)127) : 0;   // one mbarrier per (group, stage)
-  static constexpr size_t smem_bytes = carry_bytes + ring_bytes + bar_bytes;
+  static constexpr size_t smem_bytes = ring_off + ring_bytes + bar_bytes;
   static constexpr int max_blocks = (int)((227 * 1024) / (smem_bytes + 1024));
   static constexpr int min_blocks_direct = (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1));
   static constexpr int min_blocks = PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1));
-  static_assert(PF == 0 || PF * U <= LPR, "the prefetch distance must stay within one batch ahead");
+  static_assert(PF == 0 || LEAN || PF * U <= LPR, "the prefetch distance must stay within one batch ahead");
+  static_assert(!LEAN || (PF > 0 && SB % NS == 0 && sizeof(A) == 4 && U * sizeof(T) >= sizeof(A)),
+                "lean ring: the stages must divide the batch; fp32 accumulators; a stage holds a carry row");
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+// base + row * row_bytes: 32 x 32 -> 64 bit multiply-add (IMAD.WIDE.U32)
+__device__ __forceinline__ const char *row_addr(const char *base, uint32_t row, uint32_t row_bytes) {
+  return base + (uint64_t)row * row_bytes;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -203,16 +228,23 @@ segment_reduce_kernel(const Params p) {
   using SH = ShapeOf<T, VECW, LPR, VPL, PF_>;
   constexpr int PF = SH::PF;
   constexpr bool TMA = SH::TMA;
+  constexpr bool LEAN = SH::LEAN;
   constexpr int NG = SH::NG;      // chunks per tile
   constexpr int CW = SH::CW;      // columns per CTA
   constexpr int U = SH::U;        // row loads in flight per group (PF == 0) / rows per ring sub-batch
   constexpr int NS = SH::NS;
   static_assert(PF == 0 || VECW * sizeof(T) == 16, "the ring moves 16-byte pieces");
+  static_assert(!LEAN || (RED == RED_SUM && WM != WM_GENERIC), "lean ring: sum, at most one weight per edge");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A *s_head = reinterpret_cast<A *>(smem_raw);              // [NG][CW]
-  A *s_tail = s_head + NG * CW;                             // [NG][CW]
-  long long *s_head_cnt = reinterpret_cast<long long *>(s_tail + NG * CW);  // [NG]
+  // tail partial of chunk c: its own slot, or (lean ring) the start of group c's ring, which the group has
+  // drained by the time it parks a tail
+  auto tail_slot = [&](int c) -> A * {
+    if constexpr (LEAN) return reinterpret_cast<A *>(smem_raw + SH::ring_off + (size_t)c * (NS * U * CW * sizeof(T)));
+    else return reinterpret_cast<A *>(smem_raw + SH::tail_off) + c * CW;
+  };
+  long long *s_head_cnt = reinterpret_cast<long long *>(smem_raw + SH::scalars_off);  // [NG]
   long long *s_tail_cnt = s_head_cnt + NG;                  // [NG]
   int64_t *s_head_row = reinterpret_cast<int64_t *>(s_tail_cnt + NG);       // [NG]
   int64_t *s_tail_row = s_head_row + NG;                    // [NG]
@@ -264,11 +296,11 @@ segment_reduce_kernel(const Params p) {
   uint32_t ring_s = 0;
   uint32_t bars_s = 0;          // TMA: this group's NS mbarriers
   if constexpr (PF > 0) {
-    ring = reinterpret_cast<T *>(smem_raw + SH::carry_bytes) + (size_t)g * (NS * U * CW) + gl * VECW;
+    ring = reinterpret_cast<T *>(smem_raw + SH::ring_off) + (size_t)g * (NS * U * CW) + gl * VECW;
     ring_s = (uint32_t)__cvta_generic_to_shared(ring);
   }
   if constexpr (TMA) {
-    bars_s = (uint32_t)__cvta_generic_to_shared(smem_raw + SH::carry_bytes + SH::ring_bytes) + (uint32_t)(g * NS * 8);
+    bars_s = (uint32_t)__cvta_generic_to_shared(smem_raw + SH::ring_off + SH::ring_bytes) + (uint32_t)(g * NS * 8);
     if (gl == 0) {
 #pragma unroll
       for (int q = 0; q < NS; ++q) mbar_init(bars_s + q * 8, 1);
@@ -287,13 +319,13 @@ segment_reduce_kernel(const Params p) {
   int flags = 0;
 
   // parks a partial in this group's shared-memory slot (private to the group until the barrier)
-  auto park = [&](A *slot, long long *slot_cnt, int64_t *slot_row, int64_t row) {
+  auto park = [&](A *slot, long long *slot_cnt, int64_t *slot_row, int64_t row) {   // slot: this group's [CW]
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       Vec<A, VECW> t;
 #pragma unroll
       for (int i = 0; i < VECW; ++i) t.v[i] = acc[j][i];
-      *reinterpret_cast<Vec<A, VECW> *>(slot + g * CW + (j * LPR + gl) * VECW) = t;
+      *reinterpret_cast<Vec<A, VECW> *>(slot + (j * LPR + gl) * VECW) = t;
     }
     if (gl == 0) { slot_cnt[g] = cnt; slot_row[g] = row; }
   };
@@ -322,7 +354,7 @@ segment_reduce_kernel(const Params p) {
     // closes the open run, whose row is `row`
     auto close_run = [&](int64_t row) {
       if (is_head) {
-        park(s_head, s_head_cnt, s_head_row, row);
+        park(s_head + g * CW, s_head_cnt, s_head_row, row);
         flags |= FLAG_HEAD;
         is_head = false;
       } else {
@@ -346,173 +378,328 @@ segment_reduce_kernel(const Params p) {
         }
     };
 
-    // batch operands of this lane: edge (b + gl)
-    auto load_batch = [&](int64_t b, int nb, int64_t &my_dst, int64_t &my_off, A &my_w) {
-      const int64_t my_e = b + gl;
-      const bool valid = gl < nb;
-      my_dst = valid ? ld_stream(dst_index + my_e, pol) : (int64_t)-2;
-      const int64_t s = valid ? (src_index ? ld_stream(src_index + my_e, pol) : my_e) : 0;
-      my_off = s * row_bytes;
-      my_w = A(1);
-      if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + my_e, pol));
-    };
+    if constexpr (LEAN) {
+      // ---- lean ring (see ShapeOf) ---------------------------------------------------------------------
+      constexpr int SB = SH::SB;                   // sub-batches per batch; NS | SB
+      constexpr int RING_WORDS = 2 * LPR;          // operand buffers: two batches, circular
+      const int n_edges = (int)(e_end - e_begin);
+      const int nfull = n_edges / LPR;             // whole batches; a remainder only in the edge list's last chunk
+      const int n_ring = nfull * LPR;              // edges that go through the ring
+      uint32_t *ids = reinterpret_cast<uint32_t *>(smem_raw + SH::carry_bytes) + g * (2 * RING_WORDS);   // src row ids
+      float *wts = reinterpret_cast<float *>(ids + RING_WORDS);                                          // weights
+      const uint32_t row_bytes32 = (uint32_t)p.W * (uint32_t)sizeof(T);
+      uint32_t ld32 = (uint32_t)last_dst;          // dst row of the edge left of the current batch
 
-    // operands of the current batch (my_*) and of the next one (n_*); the one after that is loaded at the
-    // top of every iteration, so index / weight loads are two batches ahead of their first use
-    int64_t my_dst, my_off, n_dst = -2, n_off = 0;
-    A my_w, n_w = A(1);
-    load_batch(e_begin, (int)min((int64_t)LPR, e_end - e_begin), my_dst, my_off, my_w);
-    if (e_begin + LPR < e_end) load_batch(e_begin + LPR, (int)min((int64_t)LPR, e_end - e_begin - LPR), n_dst, n_off, n_w);
-
-    // ring: copies sub-batch [kk, kk+U) of a batch (row offsets in `offs`, one per lane) into `stage`
-    // bytes of one row inside this CTA's column slab (TMA copies exactly the slab)
-    const uint32_t slab_bytes = (uint32_t)(min((int64_t)CW, W - col0) * (int64_t)sizeof(T));
-    const char *slab_src = reinterpret_cast<const char *>(src + col0);
-    uint32_t n_consumed = 0;    // TMA: sub-batches consumed so far (stage = n % NS, parity = (n / NS) & 1)
-    auto ring_issue = [&](int64_t offs, int kk, int stage) {
-      if constexpr (TMA) {
-        // lane kk+u copies the row of edge kk+u (its own offset register) into slot (stage, u)
-        const uint32_t bar = bars_s + stage * 8;
-        if (gl == 0) mbar_expect_tx(bar, U * slab_bytes);
-        __syncwarp(gmask);          // every lane is done reading the slot's previous occupant; expect precedes the copies
-        const int u = gl - kk;
-        if (u >= 0 && u < U)
-          tma_load_1d(ring_s - (uint32_t)(gl * VECW * sizeof(T)) + (uint32_t)((stage * U + u) * CW * sizeof(T)), slab_src + offs,
-                      slab_bytes, bar);
-      } else {
+      // this lane's operands of batch bi: dst row, src row id, weight
+      auto ld_ops = [&](int bi, uint32_t &d, uint32_t &sid, float &wv) {
+        const int64_t e = e_begin + (int64_t)bi * LPR + gl;
+        d = (uint32_t)ld_stream(dst_index + e, pol);
+        sid = src_index ? (uint32_t)ld_stream(src_index + e, pol) : (uint32_t)e;
+        wv = 1.f;
+        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + e, pol));
+      };
+      // copies the U rows whose ids are at o[0..U) into ring stage st (compile-time)
+      auto issue = [&](const uint32_t *o, int st) {
+        const Vec<uint32_t, U> r = *reinterpret_cast<const Vec<uint32_t, U> *>(o);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int64_t off = __shfl_sync(gmask, offs, kk + u, LPR);
 #pragma unroll
           for (int j = 0; j < VPL; ++j)
-            cp_async_16(ring_s + (uint32_t)(((stage * U + u) * CW + j * LPR * VECW) * sizeof(T)), lane_src[j] + off);
+            cp_async_16(ring_s + (uint32_t)(((st * U + u) * CW + j * LPR * VECW) * sizeof(T)),
+                        row_addr(lane_src[j], r.v[u], row_bytes32));
+        }
+      };
+      auto add_edge = [&](const VecT(&v)[VPL], float we) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+#pragma unroll
+          for (int i = 0; i < VECW; ++i) {
+            float x = to_acc<T>(v[j].v[i]);
+            if (WM != WM_NONE) x = x * we;
+            acc[j][i] = acc[j][i] + x;
+          }
+      };
+
+      uint32_t d_cur = 0, d_nxt = 0, l_d = 0, l_s = 0;
+      float l_w = 1.f;
+      if (nfull > 0) {
+        ld_ops(0, d_cur, l_s, l_w);
+        ids[gl] = l_s;
+        wts[gl] = l_w;
+      }
+      if (nfull > 1) {
+        ld_ops(1, d_nxt, l_s, l_w);
+        ids[LPR + gl] = l_s;
+        wts[LPR + gl] = l_w;
+      }
+      __syncwarp(gmask);
+      if (nfull > 0) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {      // PF < NS <= SB: all inside batch 0
+          issue(ids + q * U, q);
+          cp_async_commit();
         }
       }
-    };
-    int stage = 0;              // ring stage of the sub-batch consumed next
-    if constexpr (PF > 0) {
-      // prologue: the first PF sub-batches of the chunk (only a full first batch uses the ring)
-      const bool full0 = (e_end - e_begin) >= LPR;
-#pragma unroll
-      for (int q = 0; q < PF; ++q) {
-        if (full0) ring_issue(my_off, q * U, q);
-        if constexpr (!TMA) cp_async_commit();
-      }
-    }
-
-    for (int64_t b = e_begin; b < e_end; b += LPR) {
-      const int nb = (int)min((int64_t)LPR, e_end - b);
-      // issue the operand loads of the batch after the next before touching this one
-      int64_t nn_dst = -2, nn_off = 0;
-      A nn_w = A(1);
-      if (b + 2 * LPR < e_end) load_batch(b + 2 * LPR, (int)min((int64_t)LPR, e_end - b - 2 * LPR), nn_dst, nn_off, nn_w);
-      const bool next_full = (e_end - b) >= 2 * LPR;
-
-      // segment heads of this batch as a bitmask (bit k: edge b+k starts a new dst row)
-      int64_t left = __shfl_up_sync(gmask, my_dst, 1, LPR);
-      if (gl == 0) left = last_dst;
-      const unsigned bmask = (__ballot_sync(gmask, gl < nb && my_dst != left) >> gshift) & low_bits<LPR>();
-      const int64_t batch_left = last_dst;
-      last_dst = __shfl_sync(gmask, my_dst, nb - 1, LPR);
-      const T *wb[VPL];                 // WM_GENERIC: this batch's weights for this lane's heads
-      const int ws_e32 = (int)p.ws_e;
-#pragma unroll
-      for (int j = 0; j < VPL; ++j) wb[j] = (WM == WM_GENERIC && lane_w[j] != nullptr) ? lane_w[j] + b * p.ws_e : nullptr;
-
-      if (nb == LPR) {
-        // ---- full batch: U loads in flight, branch-free when the U edges hold no segment head ----
+      int pos = 0;          // chunk-relative position of the current sub-batch block
+      int run_start = 0;    // chunk-relative position where the open run began
+      int slot = 0;         // word offset of the current batch in the operand buffers: 0 or LPR
 #pragma unroll 1
-        for (int k0 = 0; k0 < LPR; k0 += U) {
-          VecT v[U][VPL];
-          A w[U][VPL];
-          if constexpr (PF > 0) {
-            // keep PF sub-batches in flight: issue the one PF ahead (this batch or the next), then wait for
-            // the oldest and read this lane's own pieces back
-            const int kk = k0 + PF * U;
-            int st = stage + PF;
-            if (st >= NS) st -= NS;
-            if (kk < LPR) ring_issue(my_off, kk, st);
-            else if (next_full) ring_issue(n_off, kk - LPR, st);
-            if constexpr (TMA) {
-              mbar_wait(bars_s + stage * 8, (n_consumed / NS) & 1u);
-              ++n_consumed;
+      for (int bi = 0; bi < nfull; ++bi) {
+        const bool has_nn = bi + 2 < nfull;
+        if (has_nn) ld_ops(bi + 2, l_d, l_s, l_w);     // parked at the end of this batch, used from the next one on
+        // segment heads of this batch as a bitmask (bit k: edge k of the batch starts a new dst row)
+        uint32_t left = __shfl_up_sync(gmask, d_cur, 1, LPR);
+        if (gl == 0) left = ld32;
+        unsigned bmask = (__ballot_sync(gmask, d_cur != left) >> gshift) & low_bits<LPR>();
+        const uint32_t batch_left = ld32;
+        ld32 = __shfl_sync(gmask, d_cur, LPR - 1, LPR);
+        const int batch_pos = pos;
+#pragma unroll 1
+        for (int s0 = 0; s0 < SB; s0 += NS) {
+          const int blk = slot + s0 * U;                              // word offset of this block of NS sub-batches
+          const int blk_next = (blk + NS * U) & (RING_WORDS - 1);     // ... and of the one after (may be the next batch)
+#pragma unroll
+          for (int t = 0; t < NS; ++t) {
+            // keep PF sub-batches in flight: issue the one PF ahead (stage (t + PF) % NS, the one consumed last)
+            const int c = (t + PF) * U;
+            if (pos + c < n_ring) issue(c < NS * U ? ids + blk + c : ids + blk_next + (c - NS * U), (t + PF) % NS);
+            cp_async_commit();
+            cp_async_wait<PF>();
+            Vec<float, U> wv;
+#pragma unroll
+            for (int u = 0; u < U; ++u) wv.v[u] = 1.f;
+            if (WM == WM_EDGE) wv = *reinterpret_cast<const Vec<float, U> *>(wts + blk + t * U);
+            VecT v[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int j = 0; j < VPL; ++j)
+                v[u][j] = *reinterpret_cast<const VecT *>(ring + ((t * U + u) * CW + j * LPR * VECW));
+            const unsigned sub = bmask & low_bits<U>();
+            bmask >>= U;
+            if (sub == 0) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) add_edge(v[u], wv.v[u]);
             } else {
-              cp_async_commit();
-              cp_async_wait<PF>();
-            }
+              // a dst row starts inside these U edges: one edge at a time, operands re-read from shared memory
+#pragma unroll 1
+              for (int u = 0; u < U; ++u) {
+                const int k = pos + t * U + u;            // chunk-relative position of this edge
+                if ((sub >> u) & 1u) {
+                  const int kb = k - batch_pos;           // position inside the batch
+                  const uint32_t row = __shfl_sync(gmask, d_cur, kb > 0 ? kb - 1 : 0, LPR);
+                  cnt = k - run_start;
+                  close_run((int64_t)(kb > 0 ? row : batch_left));
+                  run_start = k;
+                }
+                VecT vv[VPL];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
-#pragma unroll
-              for (int j = 0; j < VPL; ++j) {
-                v[u][j] = *reinterpret_cast<const VecT *>(ring + ((stage * U + u) * CW + j * LPR * VECW));
-                w[u][j] = we;
-                if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
-              }
-            }
-            stage = (stage + 1 == NS) ? 0 : stage + 1;
-          } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int64_t off = __shfl_sync(gmask, my_off, k0 + u, LPR);
-              const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
-#pragma unroll
-              for (int j = 0; j < VPL; ++j) {
-                v[u][j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
-                w[u][j] = we;
-                if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
+                for (int j = 0; j < VPL; ++j)
+                  vv[j] = *reinterpret_cast<const VecT *>(ring + ((t * U + u) * CW + j * LPR * VECW));
+                add_edge(vv, WM == WM_EDGE ? wts[blk + t * U + u] : 1.f);
               }
             }
           }
-          const unsigned sub = (bmask >> k0) & low_bits<U>();
-          if (sub == 0) {
+          pos += NS * U;
+        }
+        // this batch's operand buffer is free: park batch bi+2 there
+        __syncwarp(gmask);
+        if (has_nn) {
+          ids[slot + gl] = l_s;
+          wts[slot + gl] = l_w;
+        }
+        __syncwarp(gmask);
+        slot ^= LPR;
+        d_cur = d_nxt;
+        d_nxt = l_d;
+      }
+      cp_async_wait<0>();                         // nothing of this group is in flight: its ring may hold a tail now
+      cnt = pos - run_start;
+      // remainder of the edge list's last chunk: one edge at a time, uniform operand loads
+      for (int k = pos; k < n_edges; ++k) {
+        const int64_t e = e_begin + k;
+        const uint32_t d = (uint32_t)dst_index[e];
+        const int64_t sid = src_index ? src_index[e] : e;
+        float we = 1.f;
+        if (WM == WM_EDGE) we = to_acc<T>(weight[e]);
+        VecT v[VPL];
 #pragma unroll
-            for (int u = 0; u < U; ++u) accumulate(v[u], w[u]);
-            cnt += U;
-          } else {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if ((sub >> u) & 1u) {
-                const int k = k0 + u;
-                const int64_t row = (k == 0) ? batch_left : __shfl_sync(gmask, my_dst, (k == 0) ? 0 : k - 1, LPR);
-                close_run(row);
-              }
-              accumulate(v[u], w[u]);
-              ++cnt;
-            }
+        for (int j = 0; j < VPL; ++j) v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + sid * row_bytes);
+        if (d != ld32) close_run((int64_t)ld32);
+        add_edge(v, we);
+        ++cnt;
+        ld32 = d;
+      }
+      last_dst = (int64_t)ld32;
+    } else {
+      // batch operands of this lane: edge (b + gl)
+      auto load_batch = [&](int64_t b, int nb, int64_t &my_dst, int64_t &my_off, A &my_w) {
+        const int64_t my_e = b + gl;
+        const bool valid = gl < nb;
+        my_dst = valid ? ld_stream(dst_index + my_e, pol) : (int64_t)-2;
+        const int64_t s = valid ? (src_index ? ld_stream(src_index + my_e, pol) : my_e) : 0;
+        my_off = s * row_bytes;
+        my_w = A(1);
+        if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + my_e, pol));
+      };
+
+      // operands of the current batch (my_*) and of the next one (n_*); the one after that is loaded at the
+      // top of every iteration, so index / weight loads are two batches ahead of their first use
+      int64_t my_dst, my_off, n_dst = -2, n_off = 0;
+      A my_w, n_w = A(1);
+      load_batch(e_begin, (int)min((int64_t)LPR, e_end - e_begin), my_dst, my_off, my_w);
+      if (e_begin + LPR < e_end) load_batch(e_begin + LPR, (int)min((int64_t)LPR, e_end - e_begin - LPR), n_dst, n_off, n_w);
+
+      // ring: copies sub-batch [kk, kk+U) of a batch (row offsets in `offs`, one per lane) into `stage`
+      // bytes of one row inside this CTA's column slab (TMA copies exactly the slab)
+      const uint32_t slab_bytes = (uint32_t)(min((int64_t)CW, W - col0) * (int64_t)sizeof(T));
+      const char *slab_src = reinterpret_cast<const char *>(src + col0);
+      uint32_t n_consumed = 0;    // TMA: sub-batches consumed so far (stage = n % NS, parity = (n / NS) & 1)
+      auto ring_issue = [&](int64_t offs, int kk, int stage) {
+        if constexpr (TMA) {
+          // lane kk+u copies the row of edge kk+u (its own offset register) into slot (stage, u)
+          const uint32_t bar = bars_s + stage * 8;
+          if (gl == 0) mbar_expect_tx(bar, U * slab_bytes);
+          __syncwarp(gmask);          // every lane is done reading the slot's previous occupant; expect precedes the copies
+          const int u = gl - kk;
+          if (u >= 0 && u < U)
+            tma_load_1d(ring_s - (uint32_t)(gl * VECW * sizeof(T)) + (uint32_t)((stage * U + u) * CW * sizeof(T)), slab_src + offs,
+                        slab_bytes, bar);
+        } else {
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t off = __shfl_sync(gmask, offs, kk + u, LPR);
+  #pragma unroll
+            for (int j = 0; j < VPL; ++j)
+              cp_async_16(ring_s + (uint32_t)(((stage * U + u) * CW + j * LPR * VECW) * sizeof(T)), lane_src[j] + off);
           }
         }
-      } else {
-        // ---- ragged last batch of the edge list: one edge at a time ---------------------------------
-        for (int k = 0; k < nb; ++k) {
-          const int64_t off = __shfl_sync(gmask, my_off, k, LPR);
-          const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k, LPR) : A(1);
-          const int64_t row = __shfl_sync(gmask, my_dst, k > 0 ? k - 1 : 0, LPR);
-          VecT v[VPL];
-          A w[VPL];
-#pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
-            w[j] = we;
-            if (WM == WM_GENERIC && wb[j] != nullptr) w[j] = to_acc<T>(__ldg(wb[j] + k * ws_e32));
-          }
-          if ((bmask >> k) & 1u) close_run(k == 0 ? batch_left : row);
-          accumulate(v, w);
-          ++cnt;
+      };
+      int stage = 0;              // ring stage of the sub-batch consumed next
+      if constexpr (PF > 0) {
+        // prologue: the first PF sub-batches of the chunk (only a full first batch uses the ring)
+        const bool full0 = (e_end - e_begin) >= LPR;
+  #pragma unroll
+        for (int q = 0; q < PF; ++q) {
+          if (full0) ring_issue(my_off, q * U, q);
+          if constexpr (!TMA) cp_async_commit();
         }
       }
-      my_dst = n_dst; my_off = n_off; my_w = n_w;
-      n_dst = nn_dst; n_off = nn_off; n_w = nn_w;
+
+      for (int64_t b = e_begin; b < e_end; b += LPR) {
+        const int nb = (int)min((int64_t)LPR, e_end - b);
+        // issue the operand loads of the batch after the next before touching this one
+        int64_t nn_dst = -2, nn_off = 0;
+        A nn_w = A(1);
+        if (b + 2 * LPR < e_end) load_batch(b + 2 * LPR, (int)min((int64_t)LPR, e_end - b - 2 * LPR), nn_dst, nn_off, nn_w);
+        const bool next_full = (e_end - b) >= 2 * LPR;
+
+        // segment heads of this batch as a bitmask (bit k: edge b+k starts a new dst row)
+        int64_t left = __shfl_up_sync(gmask, my_dst, 1, LPR);
+        if (gl == 0) left = last_dst;
+        const unsigned bmask = (__ballot_sync(gmask, gl < nb && my_dst != left) >> gshift) & low_bits<LPR>();
+        const int64_t batch_left = last_dst;
+        last_dst = __shfl_sync(gmask, my_dst, nb - 1, LPR);
+        const T *wb[VPL];                 // WM_GENERIC: this batch's weights for this lane's heads
+        const int ws_e32 = (int)p.ws_e;
+  #pragma unroll
+        for (int j = 0; j < VPL; ++j) wb[j] = (WM == WM_GENERIC && lane_w[j] != nullptr) ? lane_w[j] + b * p.ws_e : nullptr;
+
+        if (nb == LPR) {
+          // ---- full batch: U loads in flight, branch-free when the U edges hold no segment head ----
+  #pragma unroll 1
+          for (int k0 = 0; k0 < LPR; k0 += U) {
+            VecT v[U][VPL];
+            A w[U][VPL];
+            if constexpr (PF > 0) {
+              // keep PF sub-batches in flight: issue the one PF ahead (this batch or the next), then wait for
+              // the oldest and read this lane's own pieces back
+              const int kk = k0 + PF * U;
+              int st = stage + PF;
+              if (st >= NS) st -= NS;
+              if (kk < LPR) ring_issue(my_off, kk, st);
+              else if (next_full) ring_issue(n_off, kk - LPR, st);
+              if constexpr (TMA) {
+                mbar_wait(bars_s + stage * 8, (n_consumed / NS) & 1u);
+                ++n_consumed;
+              } else {
+                cp_async_commit();
+                cp_async_wait<PF>();
+              }
+  #pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
+  #pragma unroll
+                for (int j = 0; j < VPL; ++j) {
+                  v[u][j] = *reinterpret_cast<const VecT *>(ring + ((stage * U + u) * CW + j * LPR * VECW));
+                  w[u][j] = we;
+                  if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
+                }
+              }
+              stage = (stage + 1 == NS) ? 0 : stage + 1;
+            } else {
+  #pragma unroll
+              for (int u = 0; u < U; ++u) {
+                const int64_t off = __shfl_sync(gmask, my_off, k0 + u, LPR);
+                const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
+  #pragma unroll
+                for (int j = 0; j < VPL; ++j) {
+                  v[u][j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
+                  w[u][j] = we;
+                  if (WM == WM_GENERIC && wb[j] != nullptr) w[u][j] = to_acc<T>(__ldg(wb[j] + (k0 + u) * ws_e32));
+                }
+              }
+            }
+            const unsigned sub = (bmask >> k0) & low_bits<U>();
+            if (sub == 0) {
+  #pragma unroll
+              for (int u = 0; u < U; ++u) accumulate(v[u], w[u]);
+              cnt += U;
+            } else {
+  #pragma unroll
+              for (int u = 0; u < U; ++u) {
+                if ((sub >> u) & 1u) {
+                  const int k = k0 + u;
+                  const int64_t row = (k == 0) ? batch_left : __shfl_sync(gmask, my_dst, (k == 0) ? 0 : k - 1, LPR);
+                  close_run(row);
+                }
+                accumulate(v[u], w[u]);
+                ++cnt;
+              }
+            }
+          }
+        } else {
+          // ---- ragged last batch of the edge list: one edge at a time ---------------------------------
+          for (int k = 0; k < nb; ++k) {
+            const int64_t off = __shfl_sync(gmask, my_off, k, LPR);
+            const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k, LPR) : A(1);
+            const int64_t row = __shfl_sync(gmask, my_dst, k > 0 ? k - 1 : 0, LPR);
+            VecT v[VPL];
+            A w[VPL];
+  #pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+              v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + off);
+              w[j] = we;
+              if (WM == WM_GENERIC && wb[j] != nullptr) w[j] = to_acc<T>(__ldg(wb[j] + k * ws_e32));
+            }
+            if ((bmask >> k) & 1u) close_run(k == 0 ? batch_left : row);
+            accumulate(v, w);
+            ++cnt;
+          }
+        }
+        my_dst = n_dst; my_off = n_off; my_w = n_w;
+        n_dst = nn_dst; n_off = nn_off; n_w = nn_w;
+      }
     }
 
     // the run still open at the chunk end
     const int64_t cur_row = last_dst;
     const bool continues = (cur_row == next_row);
     if (is_head) {                      // the whole chunk is one run that entered from the left
-      park(s_head, s_head_cnt, s_head_row, cur_row);
+      park(s_head + g * CW, s_head_cnt, s_head_row, cur_row);
       flags |= FLAG_HEAD | (continues ? FLAG_THROUGH : 0);
     } else if (continues) {
-      park(s_tail, s_tail_cnt, s_tail_row, cur_row);
+      park(tail_slot(g), s_tail_cnt, s_tail_row, cur_row);
       flags |= FLAG_TAIL;
     } else {
       finalize_store(cur_row, acc, cnt);
@@ -565,7 +752,7 @@ segment_reduce_kernel(const Params p) {
     if (flags & FLAG_THROUGH) run_chain(s_head, s_head_cnt[0], s_head_row[0], 1, true);
     else run_chain(s_head, s_head_cnt[0], s_head_row[0], NG, true);
   }
-  if (flags & FLAG_TAIL) run_chain(s_tail + g * CW, s_tail_cnt[g], s_tail_row[g], g + 1, false);
+  if (flags & FLAG_TAIL) run_chain(tail_slot(g), s_tail_cnt[g], s_tail_row[g], g + 1, false);
 
   // tile-level flags follow from the index alone
   if (tid == 0 && first_col_tile) {

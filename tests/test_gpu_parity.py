@@ -199,6 +199,35 @@ def test_partition_size_does_not_change_results_beyond_tolerance(chunk, monkeypa
         assert_close(got, oracle.segment_reduce(src, si, di, w, "max"), torch.float32, "max")
 
 
+# ring variants (GEOT_B200_RING): 0 = gathered rows straight to registers, 2 / 3 = first-generation cp.async ring,
+# 35 / 39 = lean ring depth 3 / 7 (segment_reduce.cuh ShapeOf).  All walk a chunk in the same order, so sums must be
+# bit-identical across them, and every one of them is checked against the oracle.
+@pytest.mark.parametrize("ring", [2, 3, 35, 39])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_ring_variants_bit_identical_and_vs_oracle(ring, dtype, monkeypatch):
+    widths = {torch.float32: (32, 64, 100, 128, 256, 512, 1024), torch.bfloat16: (64, 128, 256, 512), torch.float16: (128, 1024)}[dtype]
+    # (E, N, skew, hub, chunk): long rows, short rows (a head in most sub-batches), a hub row cut by many chunks,
+    # and edge counts that leave a partial batch / partial chunk at the end of the list
+    graphs = [(40000 + 37, 60, 0.2, 0.0, 64), (30000 + 5, 9000, 0.0, 0.0, 32), (65536, 500, 0.6, 0.4, 128), (4099, 40, 0.0, 0.0, 256)]
+    for gi, (E, N, skew, hub, chunk) in enumerate(graphs):
+        monkeypatch.setenv("GEOT_B200_CHUNK", str(chunk))
+        si, di, g = make_graph(E, N, seed=100 * gi + ring, skew=skew, hub=hub, gaps=(gi == 1))
+        w = (torch.rand(E, generator=g) + 0.25).to(dtype)
+        for F in widths:
+            src = torch.rand(N, F, generator=g).to(dtype)
+            for name, (a_si, a_w, a_src) in {"index_scatter": (None, None, src[si]), "gather_scatter": (si, None, src),
+                                             "gather_weight_scatter": (si, w, src)}.items():
+                for reduce in ("sum", "mean"):
+                    monkeypatch.setenv("GEOT_B200_RING", "0")
+                    base = run_abi(a_src, a_si, di, a_w, reduce)
+                    monkeypatch.setenv("GEOT_B200_RING", str(ring))
+                    got = run_abi(a_src, a_si, di, a_w, reduce)
+                    what = "%s %s ring=%d F=%d graph=%d" % (name, reduce, ring, F, gi)
+                    assert torch.equal(got, base), what
+                    exp = oracle.segment_reduce(a_src, a_si, di, a_w, reduce, acc64=True)
+                    assert_close(got, exp, dtype, reduce, what)
+
+
 def test_deterministic_bit_reproducible():
     si, di, g = make_graph(300000, 2000, seed=1, skew=0.6, hub=0.1)
     w = torch.rand(300000, generator=g)

@@ -219,7 +219,7 @@ def metric_name(wk):
     return "%s effective GB/s (logical bytes / time)" % wk["op"]
 
 
-def config_of(wk, n_gpus):
+def config_of(wk, n_gpus, exchange="allgather"):
     g = wk["graph"]
     return {"workload": "%s: %s on synthetic %s-shape graph, %d nodes, %d (dst,src)-sorted edges, F=%d%s, %s" % (
                 wk["name"], wk["op"], g.name, wk["N"], wk["E"], wk["F"], (" x H=%d" % wk["H"]) if wk["H"] > 1 else "",
@@ -229,7 +229,9 @@ def config_of(wk, n_gpus):
             "bytes_logical_per_step": wk["bytes_logical"], "bytes_compulsory_per_step": wk["bytes_compulsory"],
             "l2": "per-step input streams (%.2f GB) exceed the 126 MB L2; no explicit flush" % (
                 (wk["bytes_compulsory"]) / 1e9),
-            "parallelism": "1 GPU" if n_gpus == 1 else "dst rows sharded over %d GPUs (edge-balanced), NCCL all-gather of src rows per step" % n_gpus}
+            "parallelism": "1 GPU" if n_gpus == 1 else "dst rows sharded over %d GPUs (edge-balanced); src rows per step: %s" % (
+                n_gpus, {"pipeline": "staggered NCCL send/recv steps overlapped with per-owner edge buckets",
+                         "allgather": "one NCCL all-gather, then one reduction", "none": "no exchange (edge-aligned operands)"}[exchange])}
 
 
 def run_own(args):
@@ -274,8 +276,25 @@ def run_own(args):
     out = torch.empty([l_S] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device=dev)
 
     x_full = torch.empty([N] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device=dev) if (world > 1 and wk["op"] != "index_scatter") else None
+    # N > 1, gather ops: how the src row shards travel.  "pipeline" (default): staggered NCCL send/recv steps overlapped
+    # with the reduction of per-owner edge buckets (geot_b200.dist.PipelinedGather); "allgather": one NCCL all-gather,
+    # then one reduction.  Both are inside the timed region.
+    exchange = os.environ.get("GEOT_B200_EXCHANGE", "pipeline") if (world > 1 and wk["op"] != "index_scatter") else "none"
+    if exchange == "pipeline" and H > 1:
+        exchange = "allgather"          # per-head weights: not regrouped by the pipelined path yet
+    calls_per_step = 1
+    pg = None
+    if exchange == "pipeline":
+        pg = gdist.PipelinedGather(shard)
+        pg.local_rows(x_full).copy_(x_local)
+        calls_per_step = world
+        del ws
+        ws = None
 
     def step():
+        if pg is not None:
+            pg(x_full, l_w, "sum", out=out)
+            return
         if world > 1 and wk["op"] != "index_scatter":
             xf = gdist.all_gather_rows(x_local, rb, out=x_full)
         elif world > 1:
@@ -291,7 +310,7 @@ def run_own(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    abi.profile_enable(args.steps)
+    abi.profile_enable(args.steps * calls_per_step)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -303,15 +322,15 @@ def run_own(args):
     ev[1].record()
     barrier()
     total_ms = ev[0].elapsed_time(ev[1])
-    kernel_ms = abi.profile_read(args.steps)
+    kernel_ms = abi.profile_read(args.steps * calls_per_step)     # pipelined exchange: one main-kernel launch per bucket
     abi.profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        t = torch.tensor([total_ms, sum(kernel_ms) / len(kernel_ms)], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, sum(kernel_ms) / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, kmean = t.tolist()
     else:
-        kmean = sum(kernel_ms) / len(kernel_ms)
+        kmean = sum(kernel_ms) / args.steps
     ms_per_step = total_ms / args.steps
     value = wk["bytes_logical"] / (ms_per_step * 1e-3) / 1e9
 
@@ -370,14 +389,17 @@ def run_own(args):
         e2e = {"value": round(value, 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "N > 1: operands are device-resident shards; the host-buffer entry is measured at N = 1"}
 
+    # this library's kernels per step: main + fixup per reduction; pipelined exchange adds the combine and, with
+    # weights, the edge permutation (NCCL's own copy kernels are not counted)
+    launches_per_step = 2 * calls_per_step + ((1 + (1 if l_w is not None else 0)) if pg is not None else 0)
     line = {
         "metric": metric_name(wk), "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": DTYPE_NAME[wk["dtype"]], "data": "synthetic", "config": config_of(wk, world),
+        "vs_baseline": None, "dtype": DTYPE_NAME[wk["dtype"]], "data": "synthetic", "config": config_of(wk, world, exchange),
         "edges_per_s": E / (ms_per_step * 1e-3), "frac_of_measured_hbm": round(value / peak, 4),
         "frac_of_nominal_8000": round(value / 8000.0, 4),
         "roofline": roofline, "cpu_baseline": cpu_obj, "e2e": e2e,
-        "gpu_launches": 2 * args.steps, "clocks": clocks,
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "exchange": exchange,
         "shard_imbalance": round(imbalance, 4),
     }
     print(json.dumps(line))

@@ -22,7 +22,7 @@ SYMBOLS = [
     "geot_b200_index_last", "geot_b200_plan_bytes", "geot_b200_format_preprocess", "geot_b200_plan_shards",
     "geot_b200_workspace_bytes", "geot_b200_segment_reduce", "geot_b200_index_scatter",
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
-    "geot_b200_sddmm_coo", "geot_b200_csr_to_coo",
+    "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_combine_partials", "geot_b200_permute_edges",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
 ]
 
@@ -64,6 +64,8 @@ def lib() -> ctypes.CDLL:
                                         ctypes.POINTER(GeotPlan), vp, sz, vp]
         L.geot_b200_sddmm_coo.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, vp]
         L.geot_b200_csr_to_coo.argtypes = [vp, ci, i64, i64, vp, vp]
+        L.geot_b200_combine_partials.argtypes = [vp, ci, i64, vp, i64, i64, ci, ci, vp, vp]
+        L.geot_b200_permute_edges.argtypes = [vp, vp, vp, i64, i64, vp]
         L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
         _lib = L
     return _lib
@@ -170,6 +172,27 @@ def csr_to_coo(rowptr, E):
     out = torch.empty(E, dtype=torch.int64, device=rowptr.device)
     bits = 64 if rowptr.dtype == torch.int64 else 32
     check(lib().geot_b200_csr_to_coo(_ptr(rowptr), bits, rowptr.numel() - 1, E, _ptr(out), _stream()), "csr_to_coo")
+    return out
+
+
+def combine_partials(parts, out, reduce="sum", rowptr=None):
+    """out[S, ...] = sum_k parts[k] (bucket order; / degree for mean) through geot_b200_combine_partials."""
+    n_parts, S = parts.shape[0], parts.shape[1]
+    W = 1
+    for d in parts.shape[2:]:
+        W *= d
+    check(lib().geot_b200_combine_partials(_ptr(parts), n_parts, parts.stride(0), _ptr(out), S, W, DTYPE[parts.dtype],
+                                           REDUCE[reduce], _ptr(rowptr), _stream()), "combine_partials")
+    return out
+
+
+def permute_edges(x, perm, out=None):
+    """out[e] = x[perm[e]] for a per-edge operand ([E] or [E, H]) through geot_b200_permute_edges."""
+    if out is None:
+        out = torch.empty_like(x)
+    E = perm.numel()
+    check(lib().geot_b200_permute_edges(_ptr(x), _ptr(perm), _ptr(out), E, x[0].numel() * x.element_size() if E else 2,
+                                        _stream()), "permute_edges")
     return out
 
 

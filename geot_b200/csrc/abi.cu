@@ -47,7 +47,7 @@ int env_int(const char *name, int dflt) {
 
 // `vector_ok`: rows are 16-byte addressable (per-head width multiple of the vector width and
 // 16-byte aligned base pointers); otherwise the element-wise kernels are used.
-Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok) {
+Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok, bool gather = true) {
   Config c;
   const int full = (int)(16 / dtype_size(dtype));
   const int vecw = (vector_ok && F % full == 0) ? full : 1;
@@ -73,11 +73,11 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok)
   c.shape.col_tiles = (int)((nvec + (int64_t)lpr * vpl - 1) / ((int64_t)lpr * vpl));
   c.shape.wm = 0;
   // gathered rows through the cp.async shared-memory ring for the kernels that have one (sum, 16-byte vectors, rows
-  // of >= 8 vectors).  Default: the lean ring, depth 3 (4 stages of 2 KB per warp = 6 KB in flight per warp) --
-  // profiles/r01c_*; the launcher falls back to the first-generation ring (depth 3 for 256-byte rows, 2 otherwise,
-  // profiles/r01_ring_sweep.md) where the lean ring does not apply.  GEOT_B200_RING=0 selects the register path,
-  // 2 / 3 the first-generation ring, 32 + depth a lean depth.
-  c.shape.pf = env_int("GEOT_B200_RING", (vecw > 1 && lpr >= 8) ? (geot::kLeanFlag | 3) : 0);
+  // of >= 8 vectors).  Default: the lean ring, depth 3 (4 stages of 2 KB per warp = 6 KB in flight per warp); depth 7
+  // where the rows are a pure DRAM stream (index_scatter: src row = edge id) -- profiles/r01c_ring_ab.txt.  The
+  // launcher falls back to the first-generation ring where the lean ring does not apply (fp64, per-head weights).
+  // GEOT_B200_RING=0 selects the register path, 2 / 3 the first-generation ring, 32 + depth a lean depth.
+  c.shape.pf = env_int("GEOT_B200_RING", (vecw > 1 && lpr >= 8) ? (geot::kLeanFlag | (gather ? 3 : 7)) : 0);
   const int ng = geot::kThreads / lpr;
   // Edge-count partition: every group owns `chunk` consecutive edges.  Longer chunks amortise the
   // per-chunk carry handling; shorter ones keep small inputs spread over all 148 SMs.
@@ -406,7 +406,7 @@ int segment_reduce_impl(const void *src, const int64_t *src_index, const int64_t
   }
 
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
-  const Config cfg = choose_config(E, W, F, dtype, aligned);
+  const Config cfg = choose_config(E, W, F, dtype, aligned, d_src != nullptr);
   Workspace w = carve(ws, cfg.n_tiles, W, dtype);
   if (w.bytes > ws_left) return GEOT_ERR_WORKSPACE;
 

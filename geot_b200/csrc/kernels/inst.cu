@@ -63,7 +63,7 @@ cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
             return launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DA>(p, sh, stream);
         }
       }
-      pf = (LPR == 16) ? GEOT_PF_B : GEOT_PF_A;   // not served by the lean ring: first-generation ring
+      pf = (VPL == 1) ? GEOT_PF_B : GEOT_PF_A;    // not served by the lean ring: first-generation ring (depth 3; 2 for rows >= 1 KB)
     }
     constexpr int U = ShapeOf<T, VECW, LPR, VPL, 1>::U;   // ring sub-batch
     constexpr int PFMAX = LPR / U;

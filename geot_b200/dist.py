@@ -7,6 +7,16 @@ cut into ``world_size`` contiguous dst-row ranges with balanced edge counts; ran
 reduces its own dst slice, and writes only that slice -- there is no reduction collective.  The only
 exchange is the all-gather of the src feature rows that gather ops read across shard boundaries.
 ``index_scatter`` needs no communication at all (edge-aligned data is sharded with the edges).
+
+Two forms of the exchange:
+
+* ``all_gather_rows`` + one reduction (``sharded_gather_scatter``): the whole matrix lands, then the kernel runs.
+* ``PipelinedGather``: the all-gather is unrolled into ``world-1`` staggered NCCL send/recv steps (step k: send my
+  rows to rank r-k, receive the rows of rank r+k -- every rank sends and receives exactly one shard per step, so
+  each step runs at full NVSwitch bandwidth) on a side stream, and the rank's edges are regrouped by the rank that
+  owns their src row: the bucket of the rank's own rows is reduced while shard r+1 is in flight, bucket r+k as soon
+  as step k has landed.  Buckets write partial results that one combine kernel adds in bucket order (fixed order:
+  bit-reproducible), so the exchange costs what exceeds the reduction time instead of adding to it.
 """
 from dataclasses import dataclass
 from typing import List, Optional
@@ -139,3 +149,142 @@ def sharded_index_scatter(shard: GraphShard, src_local_edges: torch.Tensor, redu
     from .index_scatter import index_scatter
     out = index_scatter(0, src_local_edges, shard.dst_index, reduce, True)
     return _pad_rows(out, shard.num_local_rows)
+
+
+# ---- exchange overlapped with the reduction -------------------------------------------------------
+
+@dataclass
+class SrcBuckets:
+    """A rank's edges regrouped by the owner of their src row, in processing order: bucket k holds the edges whose
+    src row belongs to rank ``(rank + k) % world`` (bucket 0 = the rank's own rows).  The regrouping is stable, so
+    every bucket is still sorted by dst."""
+    perm: torch.Tensor               # [E_local] position in the shard's edge list of every regrouped edge
+    bounds: List[int]                # world+1 offsets of the buckets in the regrouped arrays
+    src_index: torch.Tensor          # [E_local] regrouped
+    dst_index: torch.Tensor          # [E_local] regrouped (local dst rows)
+
+
+def bucket_by_src_owner(shard: GraphShard) -> SrcBuckets:
+    world, rank = shard.world_size, shard.rank
+    cuts = torch.tensor(shard.row_bounds[1:-1], dtype=shard.src_index.dtype, device=shard.src_index.device)
+    owner = torch.bucketize(shard.src_index, cuts, right=True)          # rb[g] <= s < rb[g+1]  <=>  owner == g
+    key = (owner - rank) % world
+    perm = torch.argsort(key, stable=True)
+    counts = torch.bincount(key, minlength=world).tolist()
+    bounds = [0]
+    for c in counts:
+        bounds.append(bounds[-1] + int(c))
+    return SrcBuckets(perm, bounds, shard.src_index[perm].contiguous(), shard.dst_index[perm].contiguous())
+
+
+class PipelinedGather:
+    """``gather_(weight_)scatter`` on a dst-row shard with the src-row exchange overlapped (sum / mean).
+
+    ``x_full`` is the caller's [N, ...] replica buffer whose OWN row range already holds this rank's rows (the
+    producer writes them there; ``local_rows(x_full)`` is that view).  Every call exchanges the other ranks' rows
+    into it while reducing.  ``reducer`` / ``combiner`` / ``permuter`` default to the C-ABI kernels; the gloo tests
+    inject CPU stand-ins to check the host logic."""
+
+    def __init__(self, shard: GraphShard, group=None, reducer=None, combiner=None, permuter=None):
+        self.shard, self.group = shard, group
+        self.world, self.rank = shard.world_size, shard.rank
+        self.buckets = bucket_by_src_owner(shard)
+        self.cuda = shard.dst_index.is_cuda
+        self._reducer, self._combiner, self._permuter = reducer, combiner, permuter
+        self._plans, self._ws, self._parts, self._wperm = {}, None, None, None
+        self._rowptr = None
+        self.comm_stream = torch.cuda.Stream() if self.cuda else None
+        self.events = [torch.cuda.Event() for _ in range(self.world)] if self.cuda else None
+
+    def local_rows(self, x_full: torch.Tensor) -> torch.Tensor:
+        rb = self.shard.row_bounds
+        return x_full[rb[self.rank]:rb[self.rank + 1]]
+
+    # -- default device kernels (C ABI) ---------------------------------------------------------------
+    def _reduce_bucket(self, k, x_full, w_b, out):
+        b = self.buckets
+        e0, e1 = b.bounds[k], b.bounds[k + 1]
+        S = self.shard.num_local_rows
+        if e1 == e0 or S == 0:
+            out.zero_()
+            return
+        si, di = b.src_index[e0:e1], b.dst_index[e0:e1]
+        if self._reducer is not None:
+            out.copy_(self._reducer(x_full, si, di, w_b, S))
+            return
+        from . import abi
+        if k not in self._plans:
+            self._plans[k] = abi.DevicePlan(di, S)
+        if self._ws is None:
+            # one scratch buffer for all buckets: the partition (hence the scratch size) is not monotonic in E
+            W = x_full[0].numel()
+            sizes = [self.buckets.bounds[i + 1] - self.buckets.bounds[i] for i in range(self.world)]
+            need = lambda n: abi.lib().geot_b200_workspace_bytes(n, W, abi.DTYPE[x_full.dtype], 1)
+            self._ws = abi.Workspace(max(sizes, key=need), W, x_full.dtype, x_full.device)
+        abi.segment_reduce(x_full, si, di, w_b, "sum", S=S, plan=self._plans[k], out=out, workspace=self._ws)
+
+    def _combine(self, parts, out, reduce):
+        if self._combiner is not None:
+            out.copy_(self._combiner(parts, reduce, self.shard.dst_index, self.shard.num_local_rows))
+            return
+        from . import abi
+        rowptr = None
+        if reduce == "mean":
+            if self._rowptr is None:
+                self._rowptr = abi.DevicePlan(self.shard.dst_index, self.shard.num_local_rows).rowptr.clone()
+            rowptr = self._rowptr
+        abi.combine_partials(parts, out, reduce, rowptr)
+
+    def _permute(self, w):
+        if self._permuter is not None:
+            return self._permuter(w, self.buckets.perm)
+        from . import abi
+        if self._wperm is None or self._wperm.shape != w.shape or self._wperm.dtype != w.dtype:
+            self._wperm = torch.empty_like(w)
+        return abi.permute_edges(w, self.buckets.perm, self._wperm)
+
+    # -- the op ---------------------------------------------------------------------------------------
+    def __call__(self, x_full: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum",
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert reduce in ("sum", "mean"), "the pipelined exchange combines partial sums: sum / mean only"
+        world, rank, rb = self.world, self.rank, self.shard.row_bounds
+        S = self.shard.num_local_rows
+        tail = list(x_full.shape[1:])
+        if out is None:
+            out = x_full.new_empty([S] + tail)
+        if self._parts is None or list(self._parts.shape[2:]) != tail or self._parts.dtype != x_full.dtype:
+            self._parts = x_full.new_empty([world, S] + tail)
+        parts = self._parts
+        x_mine = self.local_rows(x_full)
+
+        # exchange: world-1 staggered send/recv steps on the side stream
+        if self.cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())   # my rows are final; x_full's old rows were consumed
+        for k in range(1, world):
+            to, frm = (rank - k) % world, (rank + k) % world
+            ops = []
+            if x_mine.shape[0]:
+                ops.append(dist.P2POp(dist.isend, x_mine, to, self.group))
+            if rb[frm + 1] > rb[frm]:
+                ops.append(dist.P2POp(dist.irecv, x_full[rb[frm]:rb[frm + 1]], frm, self.group))
+            # (a rank with an empty row range neither sends nor is received from: both sides skip consistently)
+            if self.cuda:
+                with torch.cuda.stream(self.comm_stream):
+                    if ops:
+                        for r in dist.batch_isend_irecv(ops):
+                            r.wait()
+                    self.events[k].record(self.comm_stream)
+            elif ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+
+        # reduction: own bucket first, bucket k once step k has landed
+        w_all = self._permute(weight) if weight is not None else None
+        b = self.buckets.bounds
+        for k in range(world):
+            if k > 0 and self.cuda:
+                torch.cuda.current_stream().wait_event(self.events[k])
+            w_b = w_all[b[k]:b[k + 1]] if w_all is not None else None
+            self._reduce_bucket(k, x_full, w_b, parts[k])
+        self._combine(parts, out, reduce)
+        return out

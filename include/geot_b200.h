@@ -166,6 +166,19 @@ GEOT_API int geot_b200_sddmm_coo(const void *mat1, const int64_t *row_index, con
 GEOT_API int geot_b200_csr_to_coo(const void *rowptr, int rowptr_bits, int64_t S, int64_t E, int64_t *row_index,
                          cudaStream_t stream);
 
+/* ---- multi-GPU helpers (dst-row shards; new -- the reference has no distributed code) ---------- */
+
+/* dst[r, :] = parts[0][r, :] + parts[1][r, :] + ... (in this order; fp32 / fp64 accumulation), divided by the
+ * degree rowptr[r+1] - rowptr[r] when reduce == GEOT_MEAN.  parts: n_parts matrices [S, W] of `dtype`,
+ * part_stride elements apart.  Finishes a gather op whose edges were reduced in buckets (one per src-row owner,
+ * each while the next owner's rows were still in flight over NVLink): geot_b200/dist.py. */
+GEOT_API int geot_b200_combine_partials(const void *parts, int n_parts, int64_t part_stride, void *dst, int64_t S,
+                               int64_t W, int dtype, int reduce, const int64_t *rowptr, cudaStream_t stream);
+
+/* out[e] = in[perm[e]] for per-edge operands of bytes_per_edge bytes (even): carries weights into bucket order. */
+GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int64_t E, int64_t bytes_per_edge,
+                            cudaStream_t stream);
+
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------------- */
 
 /* Same operation with every operand in HOST memory (pinned memory makes the copies asynchronous).

@@ -64,6 +64,40 @@ def _worker(rank, world, port, q):
             local = torch.zeros(shard.num_local_rows, F)
         full = oracle.gather_weight_scatter(src_index, dst, weight, x, reduce)
         assert torch.equal(local, full[rb[rank]:rb[rank + 1]]), reduce
+    # exchange overlapped with the reduction: staggered send/recv steps + per-owner buckets + combine.  CPU stand-ins
+    # (oracle as the checker) for the three device kernels; the host logic under test is the bucketing, the step
+    # schedule and the bucket order.
+    def reducer(xf, si, di, w, S):
+        return oracle.segment_reduce(xf, si, di, w, "sum", S=S)
+
+    def combiner(parts, reduce, dst_local, S):
+        tot = parts.sum(0)
+        if reduce == "mean":
+            deg = torch.bincount(dst_local, minlength=S).clamp_min(1).to(tot.dtype)
+            tot = tot / deg.view([-1] + [1] * (tot.dim() - 1))
+        return tot
+
+    pg = gdist.PipelinedGather(shard, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm])
+    b = pg.buckets
+    assert b.bounds[0] == 0 and b.bounds[-1] == shard.num_local_edges
+    for k in range(world):
+        owner = (rank + k) % world
+        s_k = b.src_index[b.bounds[k]:b.bounds[k + 1]]
+        assert bool(((s_k >= rb[owner]) & (s_k < rb[owner + 1])).all())
+        d_k = b.dst_index[b.bounds[k]:b.bounds[k + 1]]
+        assert bool((d_k[1:] >= d_k[:-1]).all())                       # stable regrouping keeps dst order
+    for reduce in ["sum", "mean"]:
+        for wt in (None, weight):
+            x_buf = torch.full((N, F), float("nan"))
+            pg.local_rows(x_buf).copy_(x_local)
+            shard_w = shard.weight if wt is not None else None
+            got = pg(x_buf, shard_w, reduce)
+            assert torch.equal(x_buf, x)                                # the exchange rebuilt the replica
+            if wt is not None:
+                full = oracle.gather_weight_scatter(src_index, dst, weight, x, reduce)
+            else:
+                full = oracle.gather_scatter(src_index, dst, x, reduce)
+            assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), reduce
     dist.barrier()
     q.put((rank, shard.num_local_edges))
     dist.destroy_process_group()

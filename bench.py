@@ -231,7 +231,9 @@ def config_of(wk, n_gpus, exchange="allgather"):
                 (wk["bytes_compulsory"]) / 1e9),
             "parallelism": "1 GPU" if n_gpus == 1 else "dst rows sharded over %d GPUs (edge-balanced); src rows per step: %s" % (
                 n_gpus, {"pipeline": "staggered NCCL send/recv steps overlapped with per-owner edge buckets",
-                         "allgather": "one NCCL all-gather, then one reduction", "none": "no exchange (edge-aligned operands)"}[exchange])}
+                         "allgather": "one NCCL all-gather, then one reduction",
+                         "replicated": "NONE inside the step (src pre-replicated: kernel scaling only, SURVEY 8e)",
+                         "none": "no exchange (edge-aligned operands)"}[exchange])}
 
 
 def run_own(args):
@@ -282,8 +284,14 @@ def run_own(args):
     exchange = os.environ.get("GEOT_B200_EXCHANGE", "pipeline") if (world > 1 and wk["op"] != "index_scatter") else "none"
     if exchange == "pipeline" and H > 1:
         exchange = "allgather"          # per-head weights: not regrouped by the pipelined path yet
+    if exchange not in ("pipeline", "allgather", "replicated", "none"):
+        raise SystemExit("GEOT_B200_EXCHANGE must be pipeline, allgather or replicated")
     calls_per_step = 1
     pg = None
+    if exchange == "replicated":
+        # "src pre-replicated" (SURVEY 8e): every rank already holds all src rows, no exchange inside the step.  This is
+        # the kernel-scaling number reported BESIDE the default (exchange inside the timed region), never instead of it.
+        gdist.all_gather_rows(x_local, rb, out=x_full)
     if exchange == "pipeline":
         pg = gdist.PipelinedGather(shard)
         pg.local_rows(x_full).copy_(x_local)
@@ -295,7 +303,9 @@ def run_own(args):
         if pg is not None:
             pg(x_full, l_w, "sum", out=out)
             return
-        if world > 1 and wk["op"] != "index_scatter":
+        if exchange == "replicated":
+            xf = x_full
+        elif world > 1 and wk["op"] != "index_scatter":
             xf = gdist.all_gather_rows(x_local, rb, out=x_full)
         elif world > 1:
             xf = l_x_edges

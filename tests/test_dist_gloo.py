@@ -1,4 +1,4 @@
-"""world_size-2 `gloo` tests of the multi-GPU host logic (geot_b200/dist.py) on CPU.
+"""world_size-2 and -4 `gloo` tests of the multi-GPU host logic (geot_b200/dist.py) on CPU.
 
 The reduction kernels need a GPU, so here each rank reduces its shard with the CPU oracle (used as the
 checker of the sharding logic): edge-balanced bounds, local index rebasing, ragged all-gather of src
@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, hub=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -34,6 +34,8 @@ def _worker(rank, world, port, q):
     g = torch.Generator().manual_seed(0)          # same graph on every rank
     N, E, F = 301, 6000, 12
     deg_w = torch.rand(N, generator=g) ** 3         # skewed in-degrees, some zero-degree rows
+    if hub:
+        deg_w[N // 2] = 4.0 * float(deg_w.sum())    # one row holds ~80 % of the edges: some rank's row range is empty
     dst = torch.multinomial(deg_w, E, replacement=True, generator=g).sort().values
     dst[-1] = N - 1
     src_index = torch.randint(0, N, (E,), generator=g)
@@ -48,7 +50,9 @@ def _worker(rank, world, port, q):
     for gg in range(1, world):
         if 0 < eb[gg] < E:
             assert dst[eb[gg] - 1] < rb[gg] <= dst[eb[gg]]
-    assert shard.imbalance < 1.2
+    assert hub or shard.imbalance < 1.2
+    if hub:
+        assert any(rb[i] == rb[i + 1] for i in range(world))          # the case under test: an empty shard
 
     # ragged all-gather of the row shards reproduces the replicated matrix
     x_local = x[rb[rank]:rb[rank + 1]].clone()
@@ -103,12 +107,12 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_gloo():
-    world = 2
+@pytest.mark.parametrize("world,hub", [(2, False), (4, False), (4, True)])
+def test_sharding_gloo(world, hub):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, hub)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

@@ -318,6 +318,15 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # opt-in experiment (off by default): pin the src feature matrix in the persisting L2 set-aside
+    l2_note = None
+    if os.environ.get("GEOT_B200_L2_PERSIST", "0") == "1" and wk["op"] != "index_scatter":
+        try:
+            win, carve = abi.l2_persist(x_full if x_full is not None else wk["x"])
+            l2_note = "src pinned in persisting L2: window %d B, carve-out %d B" % (win, carve)
+        except abi.AbiError as e:
+            l2_note = "l2_persist unavailable: %s" % e
+
     for _ in range(max(args.warmup, 3)):
         step()
     abi.profile_enable(args.steps * calls_per_step)
@@ -412,6 +421,8 @@ def run_own(args):
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "exchange": exchange,
         "shard_imbalance": round(imbalance, 4),
     }
+    if l2_note:
+        line["config"]["l2_persist"] = l2_note
     print(json.dumps(line))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -520,6 +520,40 @@ int geot_b200_profile_read(float *ms, int capacity, int *count) {
   return GEOT_OK;
 }
 
+// ---- L2 residency hint --------------------------------------------------------------------------------
+int geot_b200_l2_persist(const void *ptr, size_t bytes, cudaStream_t stream, size_t *window_bytes, size_t *carveout_bytes) {
+  if (!ptr || bytes == 0) return GEOT_ERR_INVALID_ARG;
+  int dev = 0, max_persist = 0, max_window = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+  if (max_persist <= 0 || max_window <= 0) return GEOT_ERR_UNSUPPORTED;
+  CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+  const size_t win = std::min(bytes, (size_t)max_window);
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
+  v.accessPolicyWindow.num_bytes = win;
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
+  if (window_bytes) *window_bytes = win;
+  if (carveout_bytes) *carveout_bytes = (size_t)max_persist;
+  return GEOT_OK;
+}
+
+int geot_b200_l2_persist_reset(cudaStream_t stream) {
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.num_bytes = 0;   // a window of 0 bytes disables the policy
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
+  CUDA_TRY(cudaCtxResetPersistingL2Cache());
+  return GEOT_OK;
+}
+
 // ---- host-buffer entry ------------------------------------------------------------------------------
 // Pipeline: src first, then the sorted edge list in slices cut at segment boundaries.  Slice k+1 is
 // copied (H2D stream) while slice k is reduced (compute stream) and the finished dst rows of slice k-1

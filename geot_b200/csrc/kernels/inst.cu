@@ -15,11 +15,16 @@ cudaError_t launch_pf(const Params &p, const Shape &sh, cudaStream_t stream) {
   constexpr size_t smem = ShapeOf<T, VECW, LPR, VPL, PF>::smem_bytes;
   auto kern = segment_reduce_kernel<T, VECW, LPR, VPL, RED, WM, PF>;
   if (smem > 48 * 1024) {
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the attribute is per (function, device): one flag per instantiation and device ordinal.  A racing second
+    // thread at worst sets the same value again.
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      configured = true;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
     }
   }
   const long long blocks = (long long)p.n_tiles * sh.col_tiles;

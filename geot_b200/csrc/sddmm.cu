@@ -25,11 +25,14 @@ cudaError_t launch_sddmm(SddmmParams p, cudaStream_t stream) {
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
   auto kern = sddmm_coo_kernel<T, VECW, LPR, VPL, PF>;
   if (SH::smem_bytes > 48 * 1024) {
-    static bool configured = false;   // per instantiation
-    if (!configured) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::smem_bytes);
+    static bool configured[64] = {};   // per instantiation and device ordinal (the attribute is per device)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH::smem_bytes);
       if (e != cudaSuccess) return e;
-      configured = true;
+      if (dev >= 0 && dev < 64) configured[dev] = true;
     }
   }
   kern<<<(unsigned)blocks, kThreads, SH::smem_bytes, stream>>>(p);

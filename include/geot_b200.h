@@ -179,6 +179,19 @@ GEOT_API int geot_b200_combine_partials(const void *parts, int n_parts, int64_t 
 GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int64_t E, int64_t bytes_per_edge,
                             cudaStream_t stream);
 
+/* ---- L2 residency hint (optional) --------------------------------------------------------------------------- */
+
+/* Marks [ptr, ptr + bytes) -- the src feature matrix of a gather op -- as the persisting L2 access-policy window of
+ * `stream`: kernels launched on it afterwards keep those lines in the L2 set-aside while the read-once index /
+ * weight streams pass through.  Sets the device's persisting-L2 carve-out to its maximum; the window is clipped to
+ * the device's maximum window and the hit ratio scaled to carve-out / window when the matrix is larger.
+ * *window_bytes / *carveout_bytes (optional) receive what was applied.  GEOT_ERR_UNSUPPORTED when the device has no
+ * persisting L2.  Results never depend on it.  geot_b200_l2_persist_reset removes the window and resets the
+ * persisting lines.  Off unless the caller asks (bench.py: GEOT_B200_L2_PERSIST=1). */
+GEOT_API int geot_b200_l2_persist(const void *ptr, size_t bytes, cudaStream_t stream, size_t *window_bytes,
+                         size_t *carveout_bytes);
+GEOT_API int geot_b200_l2_persist_reset(cudaStream_t stream);
+
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------------- */
 
 /* Same operation with every operand in HOST memory (pinned memory makes the copies asynchronous).

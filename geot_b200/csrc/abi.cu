@@ -551,6 +551,7 @@ int geot_b200_l2_persist_reset(cudaStream_t stream) {
   v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
   CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
   CUDA_TRY(cudaCtxResetPersistingL2Cache());
+  CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));   // give the set-aside back to normal caching
   return GEOT_OK;
 }
 

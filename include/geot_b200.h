@@ -186,8 +186,11 @@ GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *
  * weight streams pass through.  Sets the device's persisting-L2 carve-out to its maximum; the window is clipped to
  * the device's maximum window and the hit ratio scaled to carve-out / window when the matrix is larger.
  * *window_bytes / *carveout_bytes (optional) receive what was applied.  GEOT_ERR_UNSUPPORTED when the device has no
- * persisting L2.  Results never depend on it.  geot_b200_l2_persist_reset removes the window and resets the
- * persisting lines.  Off unless the caller asks (bench.py: GEOT_B200_L2_PERSIST=1). */
+ * persisting L2.  Results never depend on it.  geot_b200_l2_persist_reset removes the window, resets the persisting
+ * lines and returns the carve-out to normal caching.  Off unless the caller asks (bench.py: GEOT_B200_L2_PERSIST=1).
+ * Measured on B200 (profiles/r01e_l2_persist_ab.txt): Reddit-shape gather_weight_scatter is SLOWER with the hint
+ * (3.52 -> 4.08 ms: the 79 MB carve-out holds 70 % of the 119 MB matrix and the rest competes for what is left),
+ * so no caller in this repo enables it by default. */
 GEOT_API int geot_b200_l2_persist(const void *ptr, size_t bytes, cudaStream_t stream, size_t *window_bytes,
                          size_t *carveout_bytes);
 GEOT_API int geot_b200_l2_persist_reset(cudaStream_t stream);

@@ -203,10 +203,10 @@ def combine_partials(parts, out, reduce="sum", rowptr=None):
 
 
 def permute_edges(x, perm, out=None):
-    """out[e] = x[perm[e]] for a per-edge operand ([E] or [E, H]) through geot_b200_permute_edges."""
-    if out is None:
-        out = torch.empty_like(x)
+    """out[e] = x[perm[e]] for a per-edge operand ([E] or [E, H]) or a row matrix through geot_b200_permute_edges."""
     E = perm.numel()
+    if out is None:
+        out = x.new_empty([E] + list(x.shape[1:]))
     check(lib().geot_b200_permute_edges(_ptr(x), _ptr(perm), _ptr(out), E, x[0].numel() * x.element_size() if E else 2,
                                         _stream()), "permute_edges")
     return out

@@ -99,6 +99,18 @@ permute_edges16_kernel(const uint16_t *__restrict__ in, const int64_t *__restric
   }
 }
 
+// 16-byte pieces: packs whole feature rows (the rows a peer asked for) at full vector width
+__global__ void __launch_bounds__(256)
+permute_rows16_kernel(const uint4 *__restrict__ in, const int64_t *__restrict__ perm, uint4 *__restrict__ out, int64_t E,
+                      int vecs) {
+  const int64_t n = E * vecs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i / vecs;
+    const int k = (int)(i - e * vecs);
+    out[i] = in[perm[e] * vecs + k];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -124,11 +136,20 @@ int geot_b200_combine_partials(const void *parts, int n_parts, int64_t part_stri
 
 int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int64_t E, int64_t bytes_per_edge,
                             cudaStream_t stream) {
-  if (!in || !perm || !out || E < 0 || bytes_per_edge <= 0 || (bytes_per_edge & 1)) return GEOT_ERR_INVALID_ARG;
-  if (E == 0) return GEOT_OK;
-  const int64_t n = E * (bytes_per_edge % 4 == 0 ? bytes_per_edge / 4 : bytes_per_edge / 2);
+  if (E < 0 || bytes_per_edge <= 0 || (bytes_per_edge & 1)) return GEOT_ERR_INVALID_ARG;
+  if (E == 0) return GEOT_OK;       // nothing to move (an empty tensor's pointer may be null)
+  if (!in || !perm || !out) return GEOT_ERR_INVALID_ARG;
+  // widest move that both the record size and the base pointers allow (a view may start mid-vector)
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out);
+  if (addr & 1) return GEOT_ERR_INVALID_ARG;
+  const bool vec16 = bytes_per_edge % 16 == 0 && (addr & 15) == 0;
+  const bool vec4 = bytes_per_edge % 4 == 0 && (addr & 3) == 0;
+  const int64_t n = E * (vec16 ? bytes_per_edge / 16 : (vec4 ? bytes_per_edge / 4 : bytes_per_edge / 2));
   const unsigned blocks = (unsigned)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
-  if (bytes_per_edge % 4 == 0)
+  if (vec16)
+    permute_rows16_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4 *>(in), perm, static_cast<uint4 *>(out), E,
+                                                      (int)(bytes_per_edge / 16));
+  else if (vec4)
     permute_edges_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint32_t *>(in), perm, static_cast<uint32_t *>(out), E,
                                                      (int)(bytes_per_edge / 4));
   else

@@ -17,6 +17,12 @@ Two forms of the exchange:
   owns their src row: the bucket of the rank's own rows is reduced while shard r+1 is in flight, bucket r+k as soon
   as step k has landed.  Buckets write partial results that one combine kernel adds in bucket order (fixed order:
   bit-reproducible), so the exchange costs what exceeds the reduction time instead of adding to it.
+* ``PipelinedGather(needed_only=True)``: the same schedule, but step k carries only the rows the receiver's edges
+  actually reference (SURVEY 8e "exchanging only the rows actually referenced").  The request lists are exchanged
+  once per graph; every call packs the requested rows per peer (one row-gather kernel) and the receiver's bucket k
+  reads them from a compact buffer through remapped src ids.  Pays off when a shard references a fraction of a
+  peer's rows (sparse, products-like graphs); on dense graphs (Reddit: every shard references almost every row)
+  it degenerates to the full exchange plus the pack.
 """
 from dataclasses import dataclass
 from typing import List, Optional
@@ -177,6 +183,66 @@ def bucket_by_src_owner(shard: GraphShard) -> SrcBuckets:
     return SrcBuckets(perm, bounds, shard.src_index[perm].contiguous(), shard.dst_index[perm].contiguous())
 
 
+@dataclass
+class NeededRows:
+    """Per-graph state of the needed-rows exchange (``PipelinedGather(needed_only=True)``)."""
+    recv_counts: List[int]           # [world] rows this rank receives from each owner (0 for itself)
+    recv_offsets: List[int]          # [world+1] their offsets in the compact receive buffer, in STEP order (rank+1, rank+2, ...)
+    send_counts: List[int]           # [world] rows each peer asked this rank for
+    send_offsets: List[int]          # [world+1] their offsets in the packed send buffer, in STEP order (rank-1, rank-2, ...)
+    send_rows: torch.Tensor          # [sum(send_counts)] LOCAL row ids to pack, grouped by peer in step order
+    src_index: torch.Tensor          # [E_local] bucket-ordered src ids: bucket 0 -> local row ids, bucket k -> row ids
+                                     #           in the compact receive buffer
+
+
+def build_needed_rows(shard: GraphShard, buckets: SrcBuckets, group=None) -> NeededRows:
+    """One-time request exchange: for every peer the sorted unique rows this rank's edges reference there.
+
+    Collectives: one all-gather of the [world] request counts, then ``world-1`` staggered send/recv steps of the
+    request lists (the same schedule the row exchange uses: works on NCCL and gloo alike)."""
+    world, rank, rb = shard.world_size, shard.rank, shard.row_bounds
+    dev, idt = buckets.src_index.device, buckets.src_index.dtype
+    b = buckets.bounds
+    src = torch.empty_like(buckets.src_index)
+    src[b[0]:b[1]] = buckets.src_index[b[0]:b[1]] - rb[rank]
+    need, recv_counts, recv_offsets = {}, [0] * world, [0]
+    for k in range(1, world):                       # step order: owner rank+k
+        g = (rank + k) % world
+        s_k = buckets.src_index[b[k]:b[k + 1]]
+        uniq = torch.unique(s_k)                    # sorted
+        need[g] = (uniq - rb[g]).contiguous()       # as the owner's local row ids
+        recv_counts[g] = int(uniq.numel())
+        src[b[k]:b[k + 1]] = recv_offsets[-1] + torch.searchsorted(uniq, s_k)
+        recv_offsets.append(recv_offsets[-1] + recv_counts[g])
+    recv_offsets.append(recv_offsets[-1])           # world+1 entries (last step has no successor)
+    # counts[r][g] = rows rank r needs from rank g
+    mine = torch.tensor(recv_counts, dtype=torch.int64, device=dev)
+    counts = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts = counts.view(world, world).cpu()
+    send_counts = [int(counts[g][rank]) for g in range(world)]
+    send_counts[rank] = 0
+    send_offsets, lists = [0], []
+    for k in range(1, world):                       # step order: I serve rank-k in step k
+        to, frm = (rank - k) % world, (rank + k) % world
+        lst = torch.empty(send_counts[to], dtype=idt, device=dev)
+        ops = []
+        if recv_counts[frm]:
+            ops.append(dist.P2POp(dist.isend, need[frm], frm, group))
+        if send_counts[to]:
+            ops.append(dist.P2POp(dist.irecv, lst, to, group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        lists.append(lst)
+        send_offsets.append(send_offsets[-1] + send_counts[to])
+    send_offsets.append(send_offsets[-1])
+    send_rows = torch.cat(lists) if lists else torch.empty(0, dtype=idt, device=dev)
+    n_local = rb[rank + 1] - rb[rank]
+    assert send_rows.numel() == 0 or (int(send_rows.min()) >= 0 and int(send_rows.max()) < n_local)
+    return NeededRows(recv_counts, recv_offsets, send_counts, send_offsets, send_rows.contiguous(), src.contiguous())
+
+
 class PipelinedGather:
     """``gather_(weight_)scatter`` on a dst-row shard with the src-row exchange overlapped (sum / mean).
 
@@ -185,7 +251,8 @@ class PipelinedGather:
     into it while reducing.  ``reducer`` / ``combiner`` / ``permuter`` default to the C-ABI kernels; the gloo tests
     inject CPU stand-ins to check the host logic."""
 
-    def __init__(self, shard: GraphShard, group=None, reducer=None, combiner=None, permuter=None):
+    def __init__(self, shard: GraphShard, group=None, reducer=None, combiner=None, permuter=None,
+                 needed_only: bool = False):
         self.shard, self.group = shard, group
         self.world, self.rank = shard.world_size, shard.rank
         self.buckets = bucket_by_src_owner(shard)
@@ -193,6 +260,9 @@ class PipelinedGather:
         self._reducer, self._combiner, self._permuter = reducer, combiner, permuter
         self._plans, self._ws, self._parts, self._wperm = {}, None, None, None
         self._rowptr = None
+        # needed_only: step k carries only the rows this rank's bucket k references (see the module docstring)
+        self.needed = build_needed_rows(shard, self.buckets, group) if needed_only else None
+        self._send_buf, self._recv_buf = None, None
         self.comm_stream = torch.cuda.Stream() if self.cuda else None
         self.events = [torch.cuda.Event() for _ in range(self.world)] if self.cuda else None
 
@@ -209,6 +279,8 @@ class PipelinedGather:
             out.zero_()
             return
         si, di = b.src_index[e0:e1], b.dst_index[e0:e1]
+        if self.needed is not None:
+            si = self.needed.src_index[e0:e1]      # ids into x_full = the rank's own rows (k == 0) / the compact buffer
         if self._reducer is not None:
             out.copy_(self._reducer(x_full, si, di, w_b, S))
             return
@@ -255,19 +327,40 @@ class PipelinedGather:
         if self._parts is None or list(self._parts.shape[2:]) != tail or self._parts.dtype != x_full.dtype:
             self._parts = x_full.new_empty([world, S] + tail)
         parts = self._parts
-        x_mine = self.local_rows(x_full)
+        nd = self.needed
+        n_local = rb[rank + 1] - rb[rank]
+        # needed_only accepts the rank's own rows [n_local, ...] as well as the [N, ...] buffer (only its own range is read)
+        x_mine = x_full if (nd is not None and x_full.shape[0] == n_local) else self.local_rows(x_full)
+        if nd is not None:
+            n_send, n_recv = nd.send_offsets[-1], nd.recv_offsets[-1]
+            if self._send_buf is None or list(self._send_buf.shape[1:]) != tail or self._send_buf.dtype != x_full.dtype:
+                self._send_buf = x_full.new_empty([max(n_send, 1)] + tail)
+                self._recv_buf = x_full.new_empty([max(n_recv, 1)] + tail)
 
         # exchange: world-1 staggered send/recv steps on the side stream
         if self.cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())   # my rows are final; x_full's old rows were consumed
+        if nd is not None and n_send:
+            if self.cuda:
+                with torch.cuda.stream(self.comm_stream):
+                    self._pack(x_mine, nd.send_rows, self._send_buf)
+            else:
+                self._pack(x_mine, nd.send_rows, self._send_buf)
         for k in range(1, world):
             to, frm = (rank - k) % world, (rank + k) % world
             ops = []
-            if x_mine.shape[0]:
-                ops.append(dist.P2POp(dist.isend, x_mine, to, self.group))
-            if rb[frm + 1] > rb[frm]:
-                ops.append(dist.P2POp(dist.irecv, x_full[rb[frm]:rb[frm + 1]], frm, self.group))
-            # (a rank with an empty row range neither sends nor is received from: both sides skip consistently)
+            if nd is None:
+                if x_mine.shape[0]:
+                    ops.append(dist.P2POp(dist.isend, x_mine, to, self.group))
+                if rb[frm + 1] > rb[frm]:
+                    ops.append(dist.P2POp(dist.irecv, x_full[rb[frm]:rb[frm + 1]], frm, self.group))
+                # (a rank with an empty row range neither sends nor is received from: both sides skip consistently)
+            else:
+                if nd.send_counts[to]:
+                    ops.append(dist.P2POp(dist.isend, self._send_buf[nd.send_offsets[k - 1]:nd.send_offsets[k]], to, self.group))
+                if nd.recv_counts[frm]:
+                    ops.append(dist.P2POp(dist.irecv, self._recv_buf[nd.recv_offsets[k - 1]:nd.recv_offsets[k]], frm, self.group))
+                # (send_counts[to] here == recv_counts[me] on rank `to`: both sides skip an empty step consistently)
             if self.cuda:
                 with torch.cuda.stream(self.comm_stream):
                     if ops:
@@ -285,6 +378,21 @@ class PipelinedGather:
             if k > 0 and self.cuda:
                 torch.cuda.current_stream().wait_event(self.events[k])
             w_b = w_all[b[k]:b[k + 1]] if w_all is not None else None
-            self._reduce_bucket(k, x_full, w_b, parts[k])
+            x_k = x_full if nd is None else (x_mine if k == 0 else self._recv_buf)
+            self._reduce_bucket(k, x_k, w_b, parts[k])
         self._combine(parts, out, reduce)
         return out
+
+    def _pack(self, x_mine, rows, out):
+        """out[i] = x_mine[rows[i]]: the rows the peers asked for, grouped by peer in step order."""
+        if self._permuter is not None:
+            out[: rows.numel()].copy_(self._permuter(x_mine, rows))
+            return
+        from . import abi
+        abi.permute_edges(x_mine, rows, out)
+
+    def exchanged_rows(self):
+        """(rows received per call, rows a full exchange would receive) -- the saving of needed_only."""
+        rb = self.shard.row_bounds
+        full = rb[-1] - (rb[self.rank + 1] - rb[self.rank])
+        return (self.needed.recv_offsets[-1] if self.needed is not None else full), full

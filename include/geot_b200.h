@@ -175,7 +175,9 @@ GEOT_API int geot_b200_csr_to_coo(const void *rowptr, int rowptr_bits, int64_t S
 GEOT_API int geot_b200_combine_partials(const void *parts, int n_parts, int64_t part_stride, void *dst, int64_t S,
                                int64_t W, int dtype, int reduce, const int64_t *rowptr, cudaStream_t stream);
 
-/* out[e] = in[perm[e]] for per-edge operands of bytes_per_edge bytes (even): carries weights into bucket order. */
+/* out[e] = in[perm[e]] for records of bytes_per_edge bytes (even): carries per-edge weights into bucket order, and
+ * packs the feature rows a peer asked for (perm = the requested local row ids, bytes_per_edge = the row size; moved
+ * as 16-byte vectors when size and pointers allow). */
 GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int64_t E, int64_t bytes_per_edge,
                             cudaStream_t stream);
 

@@ -1,0 +1,62 @@
+"""GPU parity of the device helpers of the multi-GPU path (geot_b200/csrc/exchange.cu) on ONE GPU, through the C ABI:
+permute_edges (per-edge weights into bucket order; feature rows packed for a peer -- byte moves, bit-exact) and
+combine_partials (bucket partials added in bucket order, mean by degree)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from geot_b200 import abi
+
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+@pytest.mark.parametrize("width", [1, 2, 3, 4, 8, 12, 32, 64, 65, 128, 256])
+def test_permute_edges_records(dtype, width):
+    """Records of every size class: 2-byte, 4-byte and 16-byte moves, rows selected with repeats and gaps."""
+    g = torch.Generator().manual_seed(width)
+    n_in, n_out = 1000 + width, 3000
+    x = torch.rand(n_in, width, generator=g).to(dtype)
+    if width == 1:
+        x = x.view(-1)
+    perm = torch.randint(0, n_in, (n_out,), generator=g)
+    got = abi.permute_edges(x.to(DEV), perm.to(DEV))
+    assert torch.equal(got.cpu(), x[perm])
+    # misaligned base pointers (a view one element in) must fall back to the narrower moves
+    if width >= 4 and dtype != torch.float64:
+        xx = torch.rand(n_in * width + 1, generator=g).to(dtype).to(DEV)
+        view = xx[1:].view(n_in, width)
+        got = abi.permute_edges(view, perm.to(DEV))
+        assert torch.equal(got.cpu(), view.cpu()[perm])
+
+
+def test_permute_edges_empty():
+    x = torch.rand(10, 4, device=DEV)
+    got = abi.permute_edges(x, torch.empty(0, dtype=torch.int64, device=DEV))
+    assert got.shape == (0, 4)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.float64, 1e-12), (torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("n_parts", [1, 2, 3, 8])
+@pytest.mark.parametrize("W", [1, 7, 64, 128])
+def test_combine_partials(dtype, tol, n_parts, W):
+    g = torch.Generator().manual_seed(n_parts * 1000 + W)
+    S = 777
+    parts = (torch.rand(n_parts, S, W, generator=g) + 0.5).to(dtype)
+    deg = torch.randint(0, 5, (S,), generator=g)
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)])
+    acc = parts.double().sum(0)
+    for reduce in ("sum", "mean"):
+        out = torch.empty(S, W, dtype=dtype, device=DEV)
+        abi.combine_partials(parts.to(DEV), out, reduce, rowptr.to(DEV) if reduce == "mean" else None)
+        exp = acc if reduce == "sum" else acc / deg.clamp_min(1).double().unsqueeze(-1)
+        assert ((out.cpu().double() - exp).abs() <= tol * exp.abs()).all(), (reduce, n_parts, W)
+    if dtype in (torch.float32, torch.float64):      # bucket order is the summation order: bit-exact against it
+        seq = parts[0].clone()
+        for q in range(1, n_parts):
+            seq = seq + parts[q]
+        out = torch.empty(S, W, dtype=dtype, device=DEV)
+        abi.combine_partials(parts.to(DEV), out, "sum", None)
+        assert torch.equal(out.cpu(), seq)

@@ -1,0 +1,88 @@
+"""world_size-2 NCCL test of the needed-rows exchange (``PipelinedGather(needed_only=True)``) on two GPUs (skipped
+on a one-GPU box): against the CPU oracle on the unsharded graph, bit-equal to the full pipelined exchange (same
+buckets, same summation order), on a dense and on a sparsely referencing graph."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import oracle
+    import geot_b200  # noqa: F401
+    from geot_b200 import dist as gdist
+    g = torch.Generator().manual_seed(0)          # same graph on every rank
+    N, E = 6000, 300_000
+    deg_w = torch.rand(N, generator=g) ** 3
+    dst = torch.multinomial(deg_w, E, replacement=True, generator=g).sort().values
+    dst[-1] = N - 1
+    dense = torch.randint(0, N, (E,), generator=g)
+    sparse = (torch.randint(0, 300, (E,), generator=g) * 20) % N      # 300 distinct src rows
+    weight = torch.rand(E, generator=g) + 0.25
+    for src_index in (dense, sparse):
+        for F, dtype in [(128, torch.float32), (64, torch.float32), (256, torch.bfloat16), (6, torch.float32)]:
+            x = torch.rand(N, F, generator=g).to(dtype)
+            shard = gdist.shard_graph(src_index.to(dev), dst.to(dev), weight.to(dev).to(dtype), rank, world)
+            rb = shard.row_bounds
+            x_local = x[rb[rank]:rb[rank + 1]].to(dev)
+            pf = gdist.PipelinedGather(shard)
+            pn = gdist.PipelinedGather(shard, needed_only=True)
+            got_rows, full_rows = pn.exchanged_rows()
+            assert got_rows <= full_rows and (src_index is dense or got_rows <= 300)
+            tol = 1e-5 if dtype == torch.float32 else 2e-2
+            for reduce in ("sum", "mean"):
+                for weighted in (True, False):
+                    w = shard.weight if weighted else None
+                    if weighted:
+                        full = oracle.gather_weight_scatter(src_index, dst, weight.to(dtype), x, reduce, acc64=True)
+                    else:
+                        full = oracle.gather_scatter(src_index, dst, x, reduce, acc64=True)
+                    exp = full[rb[rank]:rb[rank + 1]].double()
+                    x_full = torch.full((N, F), float("nan"), device=dev, dtype=dtype)
+                    pf.local_rows(x_full).copy_(x_local)
+                    a = pf(x_full, w, reduce).clone()
+                    b1 = pn(x_local, w, reduce).clone()
+                    b2 = pn(x_local, w, reduce)
+                    assert torch.equal(b1, b2), "needed-rows result is not bit-reproducible"
+                    assert torch.equal(a, b1), "needed-rows and full exchange differ (same buckets, same order)"
+                    bad = (b1.cpu().double() - exp).abs() > tol * exp.abs().clamp_min(1e-3 if dtype != torch.float32 else 1e-30)
+                    assert not bad.any(), (F, dtype, reduce, weighted, int(bad.sum()))
+    dist.barrier()
+    q.put(rank)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_needed_rows_nccl():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert sorted(q.get(timeout=5) for _ in range(world)) == [0, 1]

@@ -20,7 +20,8 @@ synthetic Reddit-shape graph (232,965 nodes, 114,615,892 (dst,src)-sorted edges,
 for index_scatter only -- numerically wrong, SURVEY 8a A5 -- and none for gather_weight_scatter, so the
 arm is the oracle port / torch restatement; where oracle/_ref was built its csrc/cpu kernel is timed too
 and labelled).  N > 1: one process per GPU under torchrun; the dst rows are sharded with balanced edge
-counts, each rank reduces its own slice, NCCL all-gathers the src rows each step (strong scaling).
+counts, each rank reduces its own slice, the src rows travel over NCCL each step inside the timed region
+(GEOT_B200_EXCHANGE = pipeline [default] | needed | allgather | replicated; strong scaling).
 """
 import argparse
 import json
@@ -231,6 +232,8 @@ def config_of(wk, n_gpus, exchange="allgather"):
                 (wk["bytes_compulsory"]) / 1e9),
             "parallelism": "1 GPU" if n_gpus == 1 else "dst rows sharded over %d GPUs (edge-balanced); src rows per step: %s" % (
                 n_gpus, {"pipeline": "staggered NCCL send/recv steps overlapped with per-owner edge buckets",
+                         "needed": "staggered NCCL send/recv of ONLY the rows each bucket references (packed per peer), "
+                                   "overlapped with per-owner edge buckets",
                          "allgather": "one NCCL all-gather, then one reduction",
                          "replicated": "NONE inside the step (src pre-replicated: kernel scaling only, SURVEY 8e)",
                          "none": "no exchange (edge-aligned operands)"}[exchange])}
@@ -282,18 +285,20 @@ def run_own(args):
     # with the reduction of per-owner edge buckets (geot_b200.dist.PipelinedGather); "allgather": one NCCL all-gather,
     # then one reduction.  Both are inside the timed region.
     exchange = os.environ.get("GEOT_B200_EXCHANGE", "pipeline") if (world > 1 and wk["op"] != "index_scatter") else "none"
-    if exchange == "pipeline" and H > 1:
+    if exchange in ("pipeline", "needed") and H > 1:
         exchange = "allgather"          # per-head weights: not regrouped by the pipelined path yet
-    if exchange not in ("pipeline", "allgather", "replicated", "none"):
-        raise SystemExit("GEOT_B200_EXCHANGE must be pipeline, allgather or replicated")
+    if exchange not in ("pipeline", "needed", "allgather", "replicated", "none"):
+        raise SystemExit("GEOT_B200_EXCHANGE must be pipeline, needed, allgather or replicated")
     calls_per_step = 1
     pg = None
     if exchange == "replicated":
         # "src pre-replicated" (SURVEY 8e): every rank already holds all src rows, no exchange inside the step.  This is
         # the kernel-scaling number reported BESIDE the default (exchange inside the timed region), never instead of it.
         gdist.all_gather_rows(x_local, rb, out=x_full)
-    if exchange == "pipeline":
-        pg = gdist.PipelinedGather(shard)
+    exchanged = None
+    if exchange in ("pipeline", "needed"):
+        pg = gdist.PipelinedGather(shard, needed_only=(exchange == "needed"))
+        exchanged = pg.exchanged_rows()
         pg.local_rows(x_full).copy_(x_local)
         calls_per_step = world
         del ws
@@ -410,7 +415,8 @@ def run_own(args):
 
     # this library's kernels per step: main + fixup per reduction; pipelined exchange adds the combine and, with
     # weights, the edge permutation (NCCL's own copy kernels are not counted)
-    launches_per_step = 2 * calls_per_step + ((1 + (1 if l_w is not None else 0)) if pg is not None else 0)
+    launches_per_step = (2 * calls_per_step + ((1 + (1 if l_w is not None else 0)) if pg is not None else 0)
+                         + (1 if exchange == "needed" else 0))      # needed: + the row pack
     line = {
         "metric": metric_name(wk), "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
@@ -423,6 +429,9 @@ def run_own(args):
     }
     if l2_note:
         line["config"]["l2_persist"] = l2_note
+    if exchanged is not None:
+        line["config"]["src_rows_received_per_step_rank0"] = exchanged[0]
+        line["config"]["src_rows_full_exchange_rank0"] = exchanged[1]
     print(json.dumps(line))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

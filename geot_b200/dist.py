@@ -383,6 +383,19 @@ class PipelinedGather:
         self._combine(parts, out, reduce)
         return out
 
+    def aggregate(self, x_local: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum") -> torch.Tensor:
+        """The op on this rank's OWN rows ``x_local`` (what a layer produces): the full-exchange form keeps its
+        ``[N, ...]`` replica buffer here (one per row shape / dtype) and copies the rows into their range; the
+        needed-rows form reads them in place.  Returns a new ``[n_local_rows, ...]`` tensor."""
+        if self.needed is not None:
+            return self(x_local, weight, reduce)
+        tail = list(x_local.shape[1:])
+        buf = getattr(self, "_replica", None)
+        if buf is None or list(buf.shape[1:]) != tail or buf.dtype != x_local.dtype or buf.device != x_local.device:
+            buf = self._replica = x_local.new_empty([self.shard.row_bounds[-1]] + tail)
+        self.local_rows(buf).copy_(x_local)
+        return self(buf, weight, reduce)
+
     def _pack(self, x_mine, rows, out):
         """out[i] = x_mine[rows[i]]: the rows the peers asked for, grouped by peer in step order."""
         if self._permuter is not None:

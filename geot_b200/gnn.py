@@ -15,8 +15,8 @@ PyG / torch_sparse are not part of this build, so the same math is restated on p
 
 The dense ``lin`` layers are cuBLAS GEMMs through ``torch.nn.Linear`` (library code, not part of the hot
 path).  ``forward_sharded`` runs the same stack with the node rows sharded over the GPUs of one box
-(``geot_b200.dist``): the GEMM is row-local with replicated weights, the aggregation all-gathers the src
-rows once per layer.
+(``geot_b200.dist``): the GEMM is row-local with replicated weights, the aggregation exchanges the src
+rows once per layer (one all-gather, or the pipelined / needed-rows exchange of ``PipelinedGather``).
 """
 from typing import List, Optional
 
@@ -122,21 +122,32 @@ class GraphSAGE(_Stack):
         return self._run(x, src_index, dst_index)
 
 
-def forward_sharded(model: _Stack, x_local: torch.Tensor, shard, group=None) -> torch.Tensor:
+def forward_sharded(model: _Stack, x_local: torch.Tensor, shard, group=None, gather=None) -> torch.Tensor:
     """The same stack on a dst-row shard (``geot_b200.dist.GraphShard``): ``x_local`` are this rank's node
     rows; returns this rank's rows of the output.  Per layer: row-local GEMM(s) with replicated weights,
-    one all-gather of the src rows, aggregation into the local dst rows.  ``shard.weight`` carries the
-    (globally normalised) GCN weights for a GCN stack and is ``None`` for GraphSAGE."""
+    the exchange of the src rows, aggregation into the local dst rows.  ``shard.weight`` carries the
+    (globally normalised) GCN weights for a GCN stack and is ``None`` for GraphSAGE.
+
+    ``gather``: a ``geot_b200.dist.PipelinedGather`` built once for ``shard`` -- the exchange is then overlapped
+    with the reduction (full or needed-rows form, whichever the object was built with) and its per-graph state
+    (buckets, plans, request lists) is shared by all layers.  ``None``: one all-gather per layer.  Forward only
+    (the pipelined exchange is not differentiable)."""
     from . import dist as gdist
+
+    def aggregate(h):
+        if gather is None:
+            return gdist.sharded_gather_scatter(shard, h, "sum", group)
+        return gather.aggregate(h.detach(), shard.weight, "sum")
+
     x = x_local
     for i, conv in enumerate(model.convs):
         if isinstance(conv, GCNConv):
             h = conv.lin(x)
-            out = gdist.sharded_gather_scatter(shard, h, "sum", group)
+            out = aggregate(h)
             if conv.bias is not None:
                 out = out + conv.bias
         else:
-            agg = gdist.sharded_gather_scatter(shard, x, "sum", group)
+            agg = aggregate(x)
             out = conv.lin_l(agg) + conv.lin_r(x)
         x = torch.relu(out) if i + 1 < len(model.convs) else out
     return x

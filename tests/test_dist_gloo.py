@@ -133,6 +133,23 @@ def _worker(rank, world, port, q, hub=False):
     assert p2.exchanged_rows()[0] <= 7
     got = p2(x_local.clone(), None, "sum")
     assert torch.allclose(got, oracle.gather_scatter(few, dst, x, "sum")[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6)
+    # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): every layer through the pipelined
+    # exchange (both forms), against the plain-torch restatement of the stack on the unsharded graph
+    from geot_b200 import gnn
+    torch.manual_seed(7)                                  # same random weights on every rank
+    gcn, sage = gnn.GCN(F, 16, 3), gnn.GraphSAGE(F, 16, 3)
+    norm = gnn.gcn_norm(src_index, dst, N, weight)
+    sh_gcn = gdist.shard_graph(src_index, dst, norm, rank, world, row_bounds=rb, edge_bounds=eb)
+    sh_sage = gdist.shard_graph(src_index, dst, None, rank, world, row_bounds=rb, edge_bounds=eb)
+    with torch.no_grad():
+        exp_gcn = gnn.reference_forward(gcn, x, src_index, dst, norm)[rb[rank]:rb[rank + 1]]
+        exp_sage = gnn.reference_forward(sage, x, src_index, dst)[rb[rank]:rb[rank + 1]]
+        for needed_only in (False, True):
+            kw = dict(reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm], needed_only=needed_only)
+            got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=gdist.PipelinedGather(sh_gcn, **kw))
+            assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), ("gcn", needed_only)
+            got = gnn.forward_sharded(sage, x_local, sh_sage, gather=gdist.PipelinedGather(sh_sage, **kw))
+            assert torch.allclose(got, exp_sage, rtol=1e-4, atol=1e-4), ("sage", needed_only)
     dist.barrier()
     q.put((rank, shard.num_local_edges))
     dist.destroy_process_group()

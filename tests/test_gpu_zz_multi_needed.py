@@ -68,6 +68,28 @@ def _worker(rank, world, port, q):
                     assert torch.equal(a, b1), "needed-rows and full exchange differ (same buckets, same order)"
                     bad = (b1.cpu().double() - exp).abs() > tol * exp.abs().clamp_min(1e-3 if dtype != torch.float32 else 1e-30)
                     assert not bad.any(), (F, dtype, reduce, weighted, int(bad.sum()))
+    # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): all three exchange forms against
+    # the single-GPU forward of the same stack on the unsharded graph
+    from geot_b200 import gnn
+    torch.manual_seed(7)
+    F = 64
+    x = torch.rand(N, F, generator=g)
+    gcn, sage = gnn.GCN(F, 64, 3).to(dev), gnn.GraphSAGE(F, 64, 3).to(dev)
+    si_d, di_d = dense.to(dev), dst.to(dev)
+    norm = gnn.gcn_norm(si_d, di_d, N, weight.to(dev))
+    sh_gcn = gdist.shard_graph(si_d, di_d, norm, rank, world)
+    rb = sh_gcn.row_bounds
+    sh_sage = gdist.shard_graph(si_d, di_d, None, rank, world, row_bounds=rb, edge_bounds=sh_gcn.edge_bounds)
+    x_local = x[rb[rank]:rb[rank + 1]].to(dev)
+    with torch.no_grad():
+        exp_gcn = gcn(x.to(dev), si_d, di_d, norm)[rb[rank]:rb[rank + 1]]
+        exp_sage = sage(x.to(dev), si_d, di_d)[rb[rank]:rb[rank + 1]]
+        for form in ("allgather", "pipeline", "needed"):
+            mk = lambda sh: None if form == "allgather" else gdist.PipelinedGather(sh, needed_only=(form == "needed"))
+            got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=mk(sh_gcn))
+            assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), ("gcn", form)
+            got = gnn.forward_sharded(sage, x_local, sh_sage, gather=mk(sh_sage))
+            assert torch.allclose(got, exp_sage, rtol=1e-4, atol=1e-3), ("sage", form)
     dist.barrier()
     q.put(rank)
     dist.destroy_process_group()

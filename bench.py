@@ -375,11 +375,15 @@ def run_own(args):
                         "library around it); for gathers logical bytes include L2-served re-reads of src rows (SURVEY 8d); "
                         "compulsory DRAM bytes per launch = %d" % wl.bytes_compulsory(wk["op"], l_E, l_S, N, F, H, wk["esize"])}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:       # the ncu captures are of the single-GPU launch
         try:
             roofline["traffic"] = json.load(open(tp)).get(wk["name"], {}).get("dram_bytes_per_launch")
         except Exception:
             pass
+    if roofline["traffic"]:
+        # what the DRAM interface itself carried: ncu's bytes per launch over the live launch duration
+        roofline["dram_gbs"] = round(roofline["traffic"] / (kmean * 1e-3) / 1e9, 1)
+        roofline["dram_frac_of_peak"] = round(roofline["dram_gbs"] / peak, 4)
 
     # ---- e2e: host buffers through the C-ABI host entry (N == 1) -----------------------------------------
     e2e = None

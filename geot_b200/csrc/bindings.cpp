@@ -18,6 +18,7 @@
 #include <c10/cuda/CUDAStream.h>
 #include <torch/library.h>
 
+#include <cstdlib>
 #include <list>
 #include <mutex>
 #include <string>
@@ -156,6 +157,17 @@ at::Tensor run(const char *what, const at::Tensor &src_in, const c10::optional<a
   TORCH_CHECK(dst_index.device() == src.device(), "geot::", what, ": index and src must be on the same device");
   const int64_t E = dst_index.numel();
   TORCH_CHECK(E > 0, "geot::", what, ": index is empty (the output size is index[-1] + 1)");
+  // The fast path trusts src_index like the reference does (an id >= src.size(0) is an out-of-bounds read there too).
+  // GEOT_B200_DEBUG=1 checks the range first: two reductions over the index and a host sync per call.
+  if (src_index.defined()) {
+    const char *dbg = std::getenv("GEOT_B200_DEBUG");
+    if (dbg && dbg[0] == '1') {
+      const int64_t lo = src_index.min().item<int64_t>(), hi = src_index.max().item<int64_t>();
+      TORCH_CHECK(lo >= 0 && hi < src.size(0), "geot::", what, ": src_index out of range [0, ", src.size(0), "): min ", lo,
+                  ", max ", hi);
+      TORCH_CHECK(dst_index.min().item<int64_t>() >= 0, "geot::", what, ": negative dst index");
+    }
+  }
   const int dtype = dtype_enum(src);
   auto stream = at::cuda::getCurrentCUDAStream();
 

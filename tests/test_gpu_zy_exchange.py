@@ -60,3 +60,19 @@ def test_combine_partials(dtype, tol, n_parts, W):
         out = torch.empty(S, W, dtype=dtype, device=DEV)
         abi.combine_partials(parts.to(DEV), out, "sum", None)
         assert torch.equal(out.cpu(), seq)
+
+
+def test_debug_mode_checks_src_index_range(monkeypatch):
+    """src_index is unchecked on the fast path (as in the reference); GEOT_B200_DEBUG=1 checks it."""
+    import geot_b200
+    x = torch.rand(10, 8, device=DEV)
+    di = torch.tensor([0, 0, 1, 3], device=DEV)
+    good = torch.tensor([1, 2, 3, 9], device=DEV)
+    bad = torch.tensor([1, 2, 3, 10], device=DEV)
+    monkeypatch.setenv("GEOT_B200_DEBUG", "1")
+    out = geot_b200.gather_scatter(good, di, x)
+    assert torch.equal(out[3], x[9])
+    with pytest.raises(RuntimeError, match="src_index out of range"):
+        geot_b200.gather_scatter(bad, di, x)
+    with pytest.raises(RuntimeError, match="src_index out of range"):
+        geot_b200.gather_weight_scatter(bad - 11, di, torch.rand(4, device=DEV), x)

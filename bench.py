@@ -21,7 +21,7 @@ for index_scatter only -- numerically wrong, SURVEY 8a A5 -- and none for gather
 arm is the oracle port / torch restatement; where oracle/_ref was built its csrc/cpu kernel is timed too
 and labelled).  N > 1: one process per GPU under torchrun; the dst rows are sharded with balanced edge
 counts, each rank reduces its own slice, the src rows travel over NCCL each step inside the timed region
-(GEOT_B200_EXCHANGE = pipeline [default] | needed | allgather | replicated; strong scaling).
+(GEOT_B200_EXCHANGE = pipeline [default] | needed | push | allgather | replicated; strong scaling).
 """
 import argparse
 import json
@@ -234,6 +234,8 @@ def config_of(wk, n_gpus, exchange="allgather"):
                 n_gpus, {"pipeline": "staggered NCCL send/recv steps overlapped with per-owner edge buckets",
                          "needed": "staggered NCCL send/recv of ONLY the rows each bucket references (packed per peer), "
                                    "overlapped with per-owner edge buckets",
+                         "push": "ONE kernel stores the referenced rows straight into the requesters' symmetric-memory buffers "
+                                 "over NVLink (no NCCL on the data path), overlapped with the local-src edge bucket",
                          "allgather": "one NCCL all-gather, then one reduction",
                          "replicated": "NONE inside the step (src pre-replicated: kernel scaling only, SURVEY 8e)",
                          "none": "no exchange (edge-aligned operands)"}[exchange])}
@@ -285,10 +287,10 @@ def run_own(args):
     # with the reduction of per-owner edge buckets (geot_b200.dist.PipelinedGather); "allgather": one NCCL all-gather,
     # then one reduction.  Both are inside the timed region.
     exchange = os.environ.get("GEOT_B200_EXCHANGE", "pipeline") if (world > 1 and wk["op"] != "index_scatter") else "none"
-    if exchange in ("pipeline", "needed") and H > 1:
+    if exchange in ("pipeline", "needed", "push") and H > 1:
         exchange = "allgather"          # per-head weights: not regrouped by the pipelined path yet
-    if exchange not in ("pipeline", "needed", "allgather", "replicated", "none"):
-        raise SystemExit("GEOT_B200_EXCHANGE must be pipeline, needed, allgather or replicated")
+    if exchange not in ("pipeline", "needed", "push", "allgather", "replicated", "none"):
+        raise SystemExit("GEOT_B200_EXCHANGE must be pipeline, needed, push, allgather or replicated")
     calls_per_step = 1
     pg = None
     if exchange == "replicated":
@@ -296,11 +298,12 @@ def run_own(args):
         # the kernel-scaling number reported BESIDE the default (exchange inside the timed region), never instead of it.
         gdist.all_gather_rows(x_local, rb, out=x_full)
     exchanged = None
-    if exchange in ("pipeline", "needed"):
-        pg = gdist.PipelinedGather(shard, needed_only=(exchange == "needed"))
+    if exchange in ("pipeline", "needed", "push"):
+        pg = (gdist.PeerPushGather(shard) if exchange == "push"
+              else gdist.PipelinedGather(shard, needed_only=(exchange == "needed")))
         exchanged = pg.exchanged_rows()
         pg.local_rows(x_full).copy_(x_local)
-        calls_per_step = world
+        calls_per_step = 2 if exchange == "push" else world
         del ws
         ws = None
 
@@ -420,7 +423,7 @@ def run_own(args):
     # this library's kernels per step: main + fixup per reduction; pipelined exchange adds the combine and, with
     # weights, the edge permutation (NCCL's own copy kernels are not counted)
     launches_per_step = (2 * calls_per_step + ((1 + (1 if l_w is not None else 0)) if pg is not None else 0)
-                         + (1 if exchange == "needed" else 0))      # needed: + the row pack
+                         + (1 if exchange in ("needed", "push") else 0))      # + the row pack / push kernel
     line = {
         "metric": metric_name(wk), "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",

@@ -24,7 +24,7 @@ SYMBOLS = [
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
     "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_combine_partials", "geot_b200_permute_edges",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
-    "geot_b200_l2_persist", "geot_b200_l2_persist_reset",
+    "geot_b200_l2_persist", "geot_b200_l2_persist_reset", "geot_b200_push_rows",
 ]
 
 
@@ -70,6 +70,7 @@ def lib() -> ctypes.CDLL:
         L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
         L.geot_b200_l2_persist.argtypes = [vp, sz, vp, ctypes.POINTER(sz), ctypes.POINTER(sz)]
         L.geot_b200_l2_persist_reset.argtypes = [vp]
+        L.geot_b200_push_rows.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, vp]
         _lib = L
     return _lib
 
@@ -210,6 +211,16 @@ def permute_edges(x, perm, out=None):
     check(lib().geot_b200_permute_edges(_ptr(x), _ptr(perm), _ptr(out), E, x[0].numel() * x.element_size() if E else 2,
                                         _stream()), "permute_edges")
     return out
+
+
+def push_rows(x, rows, dest_peer, dest_row, peer_bases_dev: int, aligned16: bool = True):
+    """peer_bases[dest_peer[e]][dest_row[e]] = x[rows[e]] through geot_b200_push_rows.  ``peer_bases_dev``: device
+    address of the array of per-GPU base pointers (``_SymmetricMemory.buffer_ptrs_dev``, or the ``data_ptr()`` of an
+    int64 device tensor holding the addresses)."""
+    n = rows.numel()
+    row_bytes = x[0].numel() * x.element_size() if x.shape[0] else 4
+    check(lib().geot_b200_push_rows(_ptr(x), _ptr(rows), _ptr(dest_peer), _ptr(dest_row), ctypes.c_void_p(peer_bases_dev),
+                                    n, row_bytes, 1 if aligned16 else 0, _stream()), "push_rows")
 
 
 def segment_reduce_host(src, src_index, dst_index, weight, reduce="sum", *, S, H=1, weight_layout=None, out=None):

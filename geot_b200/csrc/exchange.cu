@@ -111,6 +111,22 @@ permute_rows16_kernel(const uint4 *__restrict__ in, const int64_t *__restrict__ 
   }
 }
 
+// Fused pack + transfer over peer memory: row e of the send list goes straight into the receive buffer of the
+// GPU that asked for it -- bases[dest_peer[e]] is that GPU's buffer mapped into this process (NVLink P2P stores,
+// 16-byte vectors), dest_row[e] the row slot the receiver's src ids point at.  No staging buffer, no NCCL call.
+template <typename V>
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const V *__restrict__ x, const int64_t *__restrict__ rows, const int32_t *__restrict__ dest_peer,
+                 const int64_t *__restrict__ dest_row, V *const *__restrict__ bases, int64_t n, int vecs) {
+  const int64_t total = n * vecs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i / vecs;
+    const int k = (int)(i - e * vecs);
+    V *base = bases[dest_peer[e]];
+    base[dest_row[e] * vecs + k] = x[rows[e] * vecs + k];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -157,6 +173,28 @@ int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int6
                                                        E, (int)(bytes_per_edge / 2));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return geot_b200_set_cuda_error("permute_edges_kernel", (int)e);
+  return GEOT_OK;
+}
+
+int geot_b200_push_rows(const void *x, const int64_t *rows, const int32_t *dest_peer, const int64_t *dest_row,
+                        void *const *peer_bases, int64_t n, int64_t row_bytes, int peers_aligned16, cudaStream_t stream) {
+  if (n < 0 || row_bytes <= 0 || (row_bytes & 3)) return GEOT_ERR_INVALID_ARG;
+  if (n == 0) return GEOT_OK;
+  if (!x || !rows || !dest_peer || !dest_row || !peer_bases) return GEOT_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(x) & 3) return GEOT_ERR_INVALID_ARG;
+  // the peer bases live in device memory: the caller vouches for their alignment (symmetric allocations are)
+  const bool vec16 = row_bytes % 16 == 0 && peers_aligned16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int64_t total = n * (vec16 ? row_bytes / 16 : row_bytes / 4);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+  if (vec16)
+    push_rows_kernel<uint4><<<blocks, 256, 0, stream>>>(static_cast<const uint4 *>(x), rows, dest_peer, dest_row,
+                                                        reinterpret_cast<uint4 *const *>(peer_bases), n, (int)(row_bytes / 16));
+  else
+    push_rows_kernel<uint32_t><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t *>(x), rows, dest_peer, dest_row,
+                                                           reinterpret_cast<uint32_t *const *>(peer_bases), n,
+                                                           (int)(row_bytes / 4));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return geot_b200_set_cuda_error("push_rows_kernel", (int)e);
   return GEOT_OK;
 }
 

@@ -23,6 +23,12 @@ Two forms of the exchange:
   reads them from a compact buffer through remapped src ids.  Pays off when a shard references a fraction of a
   peer's rows (sparse, products-like graphs); on dense graphs (Reddit: every shard references almost every row)
   it degenerates to the full exchange plus the pack.
+* ``PeerPushGather``: the needed-rows exchange without NCCL on the data path.  Every rank's receive buffer is a
+  symmetric-memory allocation mapped into all processes of the box; ONE kernel per call packs the requested rows
+  and stores each straight into its slot of the requester's buffer over NVLink (``geot_b200_push_rows``), between
+  two cross-GPU barriers on a side stream, while the main stream reduces the edges whose src rows are local; the
+  remote edges are reduced when the barrier has passed, and a two-way combine finishes.  Two buckets instead of
+  ``world``: 2 reductions + 1 push + 1 combine per call whatever the GPU count.
 """
 from dataclasses import dataclass
 from typing import List, Optional
@@ -290,7 +296,7 @@ class PipelinedGather:
         if self._ws is None:
             # one scratch buffer for all buckets: the partition (hence the scratch size) is not monotonic in E
             W = x_full[0].numel()
-            sizes = [self.buckets.bounds[i + 1] - self.buckets.bounds[i] for i in range(self.world)]
+            sizes = [self.buckets.bounds[i + 1] - self.buckets.bounds[i] for i in range(len(self.buckets.bounds) - 1)]
             need = lambda n: abi.lib().geot_b200_workspace_bytes(n, W, abi.DTYPE[x_full.dtype], 1)
             self._ws = abi.Workspace(max(sizes, key=need), W, x_full.dtype, x_full.device)
         abi.segment_reduce(x_full, si, di, w_b, "sum", S=S, plan=self._plans[k], out=out, workspace=self._ws)
@@ -409,3 +415,132 @@ class PipelinedGather:
         rb = self.shard.row_bounds
         full = rb[-1] - (rb[self.rank + 1] - rb[self.rank])
         return (self.needed.recv_offsets[-1] if self.needed is not None else full), full
+
+
+class PeerPushGather(PipelinedGather):
+    """``gather_(weight_)scatter`` on a dst-row shard with the needed src rows PUSHED over peer memory (sum / mean).
+
+    Per graph: the request lists of the needed-rows exchange (``build_needed_rows``), the slot of every requested row
+    in its requester's receive buffer (``dest_peer`` / ``dest_row``), and the rank's edges split stably into two
+    dst-sorted buckets -- src row local / src row remote -- with src ids that point into ``x_local`` / the receive
+    buffer.  Per call (side stream): barrier (every peer has finished reading its buffer), one push kernel, barrier
+    (every peer's rows have landed here); (main stream): local bucket, wait, remote bucket, combine.
+
+    ``allocator(shape, dtype, device) -> (buffer, handle)``, ``pusher(x_mine, rows, dest_peer, dest_row, buffer, handle)``
+    and ``barrier(handle, channel)`` default to torch symmetric memory + the C-ABI kernel; the gloo tests inject CPU
+    stand-ins to check the host logic (slots, buckets, ordering)."""
+
+    def __init__(self, shard: GraphShard, group=None, reducer=None, combiner=None, permuter=None, allocator=None,
+                 pusher=None, barrier=None):
+        self.shard, self.group = shard, group
+        self.world, self.rank = world, rank = shard.world_size, shard.rank
+        self.cuda = shard.dst_index.is_cuda
+        self._reducer, self._combiner, self._permuter = reducer, combiner, permuter
+        self._allocator, self._pusher, self._barrier_fn = allocator, pusher, barrier
+        self._plans, self._ws, self._parts, self._wperm = {}, None, None, None
+        self._rowptr = None
+        self.needed = None                                  # (the base class's NCCL needed-rows state: not used here)
+        self._bufs = {}
+        dev = shard.dst_index.device
+        per_owner = bucket_by_src_owner(shard)
+        self.requests = nd = build_needed_rows(shard, per_owner, group)
+        E = shard.dst_index.numel()
+        # src ids in shard edge order, then the stable two-way split (local first): both halves stay dst-sorted
+        compact = torch.empty_like(nd.src_index)
+        compact[per_owner.perm] = nd.src_index
+        remote = torch.ones(E, dtype=torch.int8, device=dev)
+        remote[per_owner.perm[: per_owner.bounds[1]]] = 0
+        perm2 = torch.argsort(remote, stable=True)
+        self.buckets = SrcBuckets(perm2, [0, per_owner.bounds[1], E], compact[perm2].contiguous(),
+                                  shard.dst_index[perm2].contiguous())
+        # slots: my send segment k (for rank - k) lands at that rank's receive offset of ITS step k (owner = me)
+        mine = torch.tensor(nd.recv_offsets, dtype=torch.int64, device=dev)
+        table = torch.empty(world * (world + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(table, mine, group=group)
+        table = table.view(world, world + 1).cpu()
+        peers, slots = [], []
+        for k in range(1, world):
+            to = (rank - k) % world
+            n = nd.send_counts[to]
+            peers.append(torch.full((n,), to, dtype=torch.int32))
+            slots.append(int(table[to][k - 1]) + torch.arange(n, dtype=torch.int64))
+        self.dest_peer = (torch.cat(peers) if peers else torch.empty(0, dtype=torch.int32)).to(dev)
+        self.dest_row = (torch.cat(slots) if slots else torch.empty(0, dtype=torch.int64)).to(dev)
+        self.buffer_rows = max(int(table[:, -1].max()), 1)   # same size on every rank (symmetric allocation)
+        self.comm_stream = torch.cuda.Stream() if self.cuda else None
+        self.event = torch.cuda.Event() if self.cuda else None
+
+    # -- defaults: torch symmetric memory + the C-ABI push kernel ---------------------------------------------
+    def _buffer(self, tail, dtype, device):
+        key = (tuple(tail), dtype)
+        if key not in self._bufs:
+            shape = [self.buffer_rows] + list(tail)
+            if self._allocator is not None:
+                self._bufs[key] = self._allocator(shape, dtype, device)
+            else:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(shape, dtype=dtype, device=device)
+                hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                self._bufs[key] = (buf, hdl)
+        return self._bufs[key]
+
+    def _push(self, x_mine, buf, hdl):
+        nd = self.requests
+        if self._pusher is not None:       # (a stand-in also plays the receiving side, so it runs even with nothing to send)
+            self._pusher(x_mine, nd.send_rows, self.dest_peer, self.dest_row, buf, hdl)
+            return
+        if nd.send_rows.numel() == 0:
+            return
+        from . import abi
+        abi.push_rows(x_mine, nd.send_rows, self.dest_peer, self.dest_row, hdl.buffer_ptrs_dev)
+
+    def _barrier(self, hdl, channel):
+        if self._barrier_fn is not None:
+            self._barrier_fn(hdl, channel)
+        else:
+            hdl.barrier(channel=channel)
+
+    def aggregate(self, x_local, weight=None, reduce="sum"):
+        return self(x_local, weight, reduce)
+
+    def exchanged_rows(self):
+        rb = self.shard.row_bounds
+        return self.requests.recv_offsets[-1], rb[-1] - (rb[self.rank + 1] - rb[self.rank])
+
+    def __call__(self, x: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum",
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert reduce in ("sum", "mean"), "bucket partials are combined by addition: sum / mean only"
+        rb, rank = self.shard.row_bounds, self.rank
+        S = self.shard.num_local_rows
+        x_mine = x if x.shape[0] == S else self.local_rows(x)       # own rows, or the [N, ...] buffer holding them
+        x_mine = x_mine.contiguous()
+        tail = list(x_mine.shape[1:])
+        if out is None:
+            out = x_mine.new_empty([S] + tail)
+        if self._parts is None or list(self._parts.shape[2:]) != tail or self._parts.dtype != x_mine.dtype:
+            self._parts = x_mine.new_empty([2, S] + tail)
+        parts = self._parts
+        buf, hdl = self._buffer(tail, x_mine.dtype, x_mine.device)
+
+        def exchange():
+            self._barrier(hdl, 0)          # every peer is done reading its receive buffer (its previous call)
+            self._push(x_mine, buf, hdl)   # my rows into their slots on the peers
+            self._barrier(hdl, 1)          # every peer's rows are in my buffer
+
+        if self.cuda:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                exchange()
+                self.event.record(self.comm_stream)
+        else:
+            exchange()
+
+        w_all = self._permute(weight) if weight is not None else None
+        b = self.buckets.bounds
+        self._reduce_bucket(0, x_mine, w_all[b[0]:b[1]] if w_all is not None else None, parts[0])
+        if self.cuda:
+            torch.cuda.current_stream().wait_event(self.event)
+        self._reduce_bucket(1, buf, w_all[b[1]:b[2]] if w_all is not None else None, parts[1])
+        self._combine(parts, out, reduce)
+        return out
+

@@ -181,6 +181,17 @@ GEOT_API int geot_b200_combine_partials(const void *parts, int n_parts, int64_t 
 GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int64_t E, int64_t bytes_per_edge,
                             cudaStream_t stream);
 
+/* Fused pack + transfer over peer memory (NVLink P2P stores; no NCCL call, no staging buffer):
+ *     peer_bases[dest_peer[e]][dest_row[e], :] = x[rows[e], :]          e = 0 .. n-1,  rows of row_bytes bytes
+ * peer_bases: DEVICE array of base pointers, one per GPU of the group, each the receive buffer of that GPU mapped
+ * into this process (torch symmetric memory: _SymmetricMemory.buffer_ptrs_dev; cudaIpc / cuMem mappings work the
+ * same); peers_aligned16 != 0 promises those bases are 16-byte aligned.  row_bytes must be a multiple of 4.  The
+ * stores are complete when the kernel is; the caller orders them against the consumers with a cross-GPU barrier on
+ * `stream` (geot_b200/dist.py PeerPushGather).  rows / dest_peer / dest_row are built once per graph. */
+GEOT_API int geot_b200_push_rows(const void *x, const int64_t *rows, const int32_t *dest_peer, const int64_t *dest_row,
+                        void *const *peer_bases, int64_t n, int64_t row_bytes, int peers_aligned16,
+                        cudaStream_t stream);
+
 /* ---- L2 residency hint (optional) --------------------------------------------------------------------------- */
 
 /* Marks [ptr, ptr + bytes) -- the src feature matrix of a gather op -- as the persisting L2 access-policy window of

@@ -22,12 +22,13 @@ date +%s > $OUT/t0
 echo "== NCCL parity tests"
 timeout 400 python -m pytest tests/test_gpu_multi.py tests/test_gpu_zz_multi_needed.py -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_multi.txt
 run reddit_gws_pipeline X=1 -- --steps 10 --warmup 3
-for ex in pipeline needed allgather replicated; do
+for ex in pipeline needed push allgather replicated; do
   run products_gs64_$ex GEOT_B200_EXCHANGE=$ex -- --workload products_gs64 --steps 10 --warmup 3
 done
-for ex in pipeline needed replicated; do
+for ex in pipeline needed push replicated; do
   run products_gs256_$ex GEOT_B200_EXCHANGE=$ex -- --workload products_gs256 --steps 10 --warmup 3
 done
+run reddit_gws_push GEOT_B200_EXCHANGE=push -- --steps 10 --warmup 3
 run reddit_gws_needed GEOT_B200_EXCHANGE=needed -- --steps 10 --warmup 3
 run reddit_gws_allgather GEOT_B200_EXCHANGE=allgather -- --steps 10 --warmup 3
 run reddit_gws_replicated GEOT_B200_EXCHANGE=replicated -- --steps 10 --warmup 3

@@ -133,6 +133,49 @@ def _worker(rank, world, port, q, hub=False):
     assert p2.exchanged_rows()[0] <= 7
     got = p2(x_local.clone(), None, "sum")
     assert torch.allclose(got, oracle.gather_scatter(few, dst, x, "sum")[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6)
+    # peer-push form: ONE push of the requested rows into slots of the requesters' buffers, two buckets.  The stand-in
+    # pusher ships (slot, row) pairs over gloo and the RECEIVER stores each row where the SENDER's slot says, so the
+    # slot arithmetic (dest_peer / dest_row), the two-way bucket split and its src ids are what is under test.
+    holder = {}
+
+    def pusher(x_mine, rows, dest_peer, dest_row, buf, hdl):
+        pp, ops, inbox = holder["pp"], [], {}
+        for p in range(world):
+            if p == rank:
+                continue
+            m = dest_peer == p
+            if int(m.sum()):
+                ops.append(dist.P2POp(dist.isend, dest_row[m].contiguous(), p, tag=1))
+                ops.append(dist.P2POp(dist.isend, x_mine[rows[m]].contiguous(), p, tag=2))
+            n = pp.requests.recv_counts[p]
+            if n:
+                inbox[p] = (torch.empty(n, dtype=torch.int64), torch.empty([n] + list(x_mine.shape[1:]), dtype=x_mine.dtype))
+                ops.append(dist.P2POp(dist.irecv, inbox[p][0], p, tag=1))
+                ops.append(dist.P2POp(dist.irecv, inbox[p][1], p, tag=2))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        for p, (slots, data) in inbox.items():
+            assert slots.numel() == torch.unique(slots).numel() and int(slots.max()) < buf.shape[0]
+            buf[slots] = data
+
+    kw_push = dict(reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm], pusher=pusher,
+                   allocator=lambda shape, dtype, device: (torch.full(shape, float("nan"), dtype=dtype), None),
+                   barrier=lambda hdl, channel: dist.barrier())
+    pp = holder["pp"] = gdist.PeerPushGather(shard, **kw_push)
+    assert pp.buckets.bounds[0] == 0 and pp.buckets.bounds[2] == shard.num_local_edges
+    for k in range(2):
+        d_k = pp.buckets.dst_index[pp.buckets.bounds[k]:pp.buckets.bounds[k + 1]]
+        assert bool((d_k[1:] >= d_k[:-1]).all())
+    assert pp.exchanged_rows() == pn.exchanged_rows()
+    for reduce in ["sum", "mean"]:
+        for wt in (None, weight):
+            for _ in range(2):                                          # twice: the buffer is reused across calls
+                got = pp(x_local.clone(), shard.weight if wt is not None else None, reduce)
+            full = (oracle.gather_weight_scatter(src_index, dst, weight, x, reduce) if wt is not None
+                    else oracle.gather_scatter(src_index, dst, x, reduce))
+            assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), ("push", reduce)
+
     # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): every layer through the pipelined
     # exchange (both forms), against the plain-torch restatement of the stack on the unsharded graph
     from geot_b200 import gnn
@@ -150,6 +193,9 @@ def _worker(rank, world, port, q, hub=False):
             assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), ("gcn", needed_only)
             got = gnn.forward_sharded(sage, x_local, sh_sage, gather=gdist.PipelinedGather(sh_sage, **kw))
             assert torch.allclose(got, exp_sage, rtol=1e-4, atol=1e-4), ("sage", needed_only)
+        holder["pp"] = gdist.PeerPushGather(sh_gcn, **kw_push)
+        got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=holder["pp"])
+        assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), "gcn push"
     dist.barrier()
     q.put((rank, shard.num_local_edges))
     dist.destroy_process_group()

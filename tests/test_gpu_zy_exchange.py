@@ -76,3 +76,30 @@ def test_debug_mode_checks_src_index_range(monkeypatch):
         geot_b200.gather_scatter(bad, di, x)
     with pytest.raises(RuntimeError, match="src_index out of range"):
         geot_b200.gather_weight_scatter(bad - 11, di, torch.rand(4, device=DEV), x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("width", [2, 6, 8, 64, 128, 130])
+def test_push_rows_into_peer_buffers(dtype, width):
+    """geot_b200_push_rows on one GPU: the "peers" are three local buffers whose base pointers sit in a device array,
+    exactly as symmetric memory presents the mapped buffers of the other GPUs.  Byte moves: bit-exact."""
+    if width * torch.tensor([], dtype=dtype).element_size() % 4:
+        pytest.skip("rows are moved in 4-byte words")
+    g = torch.Generator().manual_seed(width)
+    n_in, n = 500, 2000
+    x = torch.rand(n_in, width, generator=g).to(dtype).to(DEV)
+    rows = torch.randint(0, n_in, (n,), generator=g)
+    peer = torch.randint(0, 3, (n,), generator=g).to(torch.int32)
+    slot = torch.empty(n, dtype=torch.int64)
+    for p in range(3):                                           # distinct slots per peer, in random order
+        m = peer == p
+        slot[m] = torch.randperm(int(m.sum()) + 5, generator=g)[: int(m.sum())]
+    bufs = [torch.full((int((peer == p).sum()) + 5, width), -1.0, dtype=dtype, device=DEV) for p in range(3)]
+    bases = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    abi.push_rows(x, rows.to(DEV), peer.to(DEV), slot.to(DEV), bases.data_ptr(), aligned16=True)
+    torch.cuda.synchronize()
+    for p in range(3):
+        exp = torch.full(bufs[p].shape, -1.0, dtype=dtype)
+        m = peer == p
+        exp[slot[m]] = x.cpu()[rows[m]]
+        assert torch.equal(bufs[p].cpu(), exp)

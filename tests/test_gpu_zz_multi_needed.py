@@ -1,6 +1,8 @@
-"""world_size-2 NCCL test of the needed-rows exchange (``PipelinedGather(needed_only=True)``) on two GPUs (skipped
-on a one-GPU box): against the CPU oracle on the unsharded graph, bit-equal to the full pipelined exchange (same
-buckets, same summation order), on a dense and on a sparsely referencing graph."""
+"""world_size-2 test of the needed-rows exchanges on two GPUs (skipped on a one-GPU box): the NCCL form
+(``PipelinedGather(needed_only=True)``: bit-equal to the full pipelined exchange -- same buckets, same summation
+order) and the peer-memory form (``PeerPushGather``: symmetric memory + ``geot_b200_push_rows``), against the CPU
+oracle on the unsharded graph, on a dense and on a sparsely referencing graph; then the sharded 3-layer GCN /
+GraphSAGE forward through every exchange form."""
 import os
 import socket
 import sys
@@ -48,6 +50,8 @@ def _worker(rank, world, port, q):
             x_local = x[rb[rank]:rb[rank + 1]].to(dev)
             pf = gdist.PipelinedGather(shard)
             pn = gdist.PipelinedGather(shard, needed_only=True)
+            pp = gdist.PeerPushGather(shard)          # symmetric memory + geot_b200_push_rows (no NCCL on the data path)
+            assert pp.exchanged_rows() == pn.exchanged_rows()
             got_rows, full_rows = pn.exchanged_rows()
             assert got_rows <= full_rows and (src_index is dense or got_rows <= 300)
             tol = 1e-5 if dtype == torch.float32 else 2e-2
@@ -68,6 +72,11 @@ def _worker(rank, world, port, q):
                     assert torch.equal(a, b1), "needed-rows and full exchange differ (same buckets, same order)"
                     bad = (b1.cpu().double() - exp).abs() > tol * exp.abs().clamp_min(1e-3 if dtype != torch.float32 else 1e-30)
                     assert not bad.any(), (F, dtype, reduce, weighted, int(bad.sum()))
+                    c1 = pp(x_local, w, reduce).clone()
+                    c2 = pp(x_local, w, reduce)
+                    assert torch.equal(c1, c2), "peer-push result is not bit-reproducible"
+                    bad = (c1.cpu().double() - exp).abs() > tol * exp.abs().clamp_min(1e-3 if dtype != torch.float32 else 1e-30)
+                    assert not bad.any(), ("push", F, dtype, reduce, weighted, int(bad.sum()))
     # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): all three exchange forms against
     # the single-GPU forward of the same stack on the unsharded graph
     from geot_b200 import gnn
@@ -84,8 +93,9 @@ def _worker(rank, world, port, q):
     with torch.no_grad():
         exp_gcn = gcn(x.to(dev), si_d, di_d, norm)[rb[rank]:rb[rank + 1]]
         exp_sage = sage(x.to(dev), si_d, di_d)[rb[rank]:rb[rank + 1]]
-        for form in ("allgather", "pipeline", "needed"):
-            mk = lambda sh: None if form == "allgather" else gdist.PipelinedGather(sh, needed_only=(form == "needed"))
+        for form in ("allgather", "pipeline", "needed", "push"):
+            mk = lambda sh: (None if form == "allgather" else gdist.PeerPushGather(sh) if form == "push"
+                             else gdist.PipelinedGather(sh, needed_only=(form == "needed")))
             got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=mk(sh_gcn))
             assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), ("gcn", form)
             got = gnn.forward_sharded(sage, x_local, sh_sage, gather=mk(sh_sage))

@@ -478,9 +478,17 @@ class PeerPushGather(PipelinedGather):
             if self._allocator is not None:
                 self._bufs[key] = self._allocator(shape, dtype, device)
             else:
+                import warnings
                 import torch.distributed._symmetric_memory as symm
+                pg = self.group if self.group is not None else dist.group.WORLD
+                try:        # older torch wants the group registered first; newer ones do it in rendezvous
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        symm.enable_symm_mem_for_group(pg.group_name)
+                except Exception:
+                    pass
                 buf = symm.empty(shape, dtype=dtype, device=device)
-                hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+                hdl = symm.rendezvous(buf, pg)
                 self._bufs[key] = (buf, hdl)
         return self._bufs[key]
 

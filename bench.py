@@ -410,8 +410,15 @@ def run_own(args):
             call()
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / n_e2e
+        try:        # what the last call really moved (differs from the operand sizes under GEOT_B200_HOST_COMPACT)
+            h2d, d2h = abi.host_last_transfer()
+        except Exception:
+            pass
         e2e = {"value": round(wk["bytes_logical"] / e2e_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3), "steps": n_e2e,
+               "transport": {"0": "operands as given", "1": "row pointers instead of dst_index",
+                             "2": "int32 src_index", "3": "row pointers + int32 src_index"}.get(
+                                 os.environ.get("GEOT_B200_HOST_COMPACT", "0"), "operands as given"),
                "edges_per_s": E / e2e_s,
                "api": "geot_b200_segment_reduce_host (C ABI, pinned host operands; H2D + kernels + D2H timed, host wall clock)"}
         cpu_obj, _ = cpu_arm(wk, 1, 3)

@@ -25,6 +25,7 @@ SYMBOLS = [
     "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_combine_partials", "geot_b200_permute_edges",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
     "geot_b200_l2_persist", "geot_b200_l2_persist_reset", "geot_b200_push_rows",
+    "geot_b200_host_last_transfer", "geot_b200_host_row_pointers",
 ]
 
 
@@ -71,6 +72,8 @@ def lib() -> ctypes.CDLL:
         L.geot_b200_l2_persist.argtypes = [vp, sz, vp, ctypes.POINTER(sz), ctypes.POINTER(sz)]
         L.geot_b200_l2_persist_reset.argtypes = [vp]
         L.geot_b200_push_rows.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, vp]
+        L.geot_b200_host_last_transfer.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
+        L.geot_b200_host_row_pointers.argtypes = [vp, i64, i64, i64, vp, ci]
         _lib = L
     return _lib
 
@@ -221,6 +224,21 @@ def push_rows(x, rows, dest_peer, dest_row, peer_bases_dev: int, aligned16: bool
     row_bytes = x[0].numel() * x.element_size() if x.shape[0] else 4
     check(lib().geot_b200_push_rows(_ptr(x), _ptr(rows), _ptr(dest_peer), _ptr(dest_row), ctypes.c_void_p(peer_bases_dev),
                                     n, row_bytes, 1 if aligned16 else 0, _stream()), "push_rows")
+
+
+def host_last_transfer():
+    """(h2d_bytes, d2h_bytes) the last segment_reduce_host call moved over the link."""
+    a, b = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    check(lib().geot_b200_host_last_transfer(ctypes.byref(a), ctypes.byref(b)), "host_last_transfer")
+    return a.value, b.value
+
+
+def host_row_pointers(index: torch.Tensor, row0: int, rows: int, threads: int = 0) -> torch.Tensor:
+    """CSR row pointer [rows + 1] of a sorted CPU index slice through geot_b200_host_row_pointers (pure host code)."""
+    assert not index.is_cuda and index.dtype == torch.int64 and index.is_contiguous()
+    out = torch.empty(rows + 1, dtype=torch.int64)
+    check(lib().geot_b200_host_row_pointers(_ptr(index), index.numel(), row0, rows, _ptr(out), threads), "host_row_pointers")
+    return out
 
 
 def segment_reduce_host(src, src_index, dst_index, weight, reduce="sum", *, S, H=1, weight_layout=None, out=None):

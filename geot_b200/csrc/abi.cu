@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
+#include <vector>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/geot_b200.h"
@@ -222,6 +224,47 @@ __global__ void csr_rows_kernel(const P *__restrict__ rowptr, int64_t S, int64_t
     if ((int64_t)rowptr[mid] <= e) lo = mid; else hi = mid;
   }
   row[e] = lo;
+}
+
+// int32 -> int64 (compact host transport of src_index, geot_b200_segment_reduce_host)
+__global__ void widen_index_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// fn(begin, end) over [0, n) on up to `threads` host threads (the calling thread takes the first share)
+template <typename F>
+void parallel_ranges(int threads, int64_t n, F fn) {
+  if (n <= 0) return;
+  threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n / 4096 + 1));
+  if (threads == 1) { fn((int64_t)0, n); return; }
+  std::vector<std::thread> pool;
+  const int64_t per = (n + threads - 1) / threads;
+  for (int t = 1; t < threads; ++t) {
+    const int64_t b = per * t, e = std::min(n, b + per);
+    if (b < e) pool.emplace_back([=] { fn(b, e); });
+  }
+  fn((int64_t)0, std::min(n, per));
+  for (auto &th : pool) th.join();
+}
+
+// rp[i] = first position in idx[0, n) whose value is >= row0 + i, for i in [0, rows]  (idx sorted): the slice's CSR
+// row pointer.  Rows are walked in order, galloping from the previous boundary, so the cost follows the number of
+// cache lines a row spans rather than log2(n) misses per row.
+void host_row_pointers(const int64_t *idx, int64_t n, int64_t row0, int64_t rows, int64_t *rp, int threads) {
+  parallel_ranges(threads, rows + 1, [=](int64_t ia, int64_t ib) {
+    int64_t pos = std::lower_bound(idx, idx + n, row0 + ia) - idx;
+    for (int64_t i = ia; i < ib; ++i) {
+      const int64_t target = row0 + i;
+      if (pos < n && idx[pos] < target) {
+        int64_t lo = pos, step = 1;
+        while (lo + step < n && idx[lo + step] < target) { lo += step; step <<= 1; }
+        const int64_t hi = std::min(n, lo + step);
+        pos = std::lower_bound(idx + lo + 1, idx + hi, target) - idx;
+      }
+      rp[i] = pos;
+    }
+  });
 }
 
 // ---- instrumentation: event pairs around the main kernel ------------------------------------------
@@ -568,13 +611,18 @@ struct Arena {
   static constexpr int kMaxSlices = 64;
   cudaEvent_t copied[kMaxSlices] = {}, reduced[kMaxSlices] = {};
   cudaEvent_t src_ready = nullptr;
+  char *pinned = nullptr;         // compact transport: host staging (row pointers, narrowed src ids), double-buffered
+  size_t pinned_bytes = 0;
+  unsigned long long last_h2d = 0, last_d2h = 0;   // bytes the last call moved over the link
 };
 Arena g_arena;
+
 }  // namespace
 
 int geot_b200_host_arena_release(void) {
   Arena &a = g_arena;
   if (a.base) cudaFree(a.base);
+  if (a.pinned) cudaFreeHost(a.pinned);
   for (int i = 0; i < Arena::kMaxSlices; ++i) {
     if (a.copied[i]) cudaEventDestroy(a.copied[i]);
     if (a.reduced[i]) cudaEventDestroy(a.reduced[i]);
@@ -621,9 +669,26 @@ int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t 
   int64_t max_slice = 0;
   for (int k = 0; k < n_slices; ++k) max_slice = std::max(max_slice, cut[k + 1] - cut[k]);
 
+  // Compact transport (GEOT_B200_HOST_COMPACT bit mask, off by default): 1 = send each slice's CSR row pointer
+  // (rows + 1 values, computed on the host threads) instead of its dst_index (one value per edge) and expand it on
+  // the device; 2 = send src_index as int32 (narrowed on the host threads, widened on the device).  Same results;
+  // Reddit-shape gws: 2.41 GB -> 1.49 GB (1) -> 1.04 GB (3) over the link per call.
+  int compact = env_int("GEOT_B200_HOST_COMPACT", 0);
+  if (!gather || N_src > 0x7fffffffLL) compact &= ~2;
+  const bool c_rows = (compact & 1) != 0, c_src32 = (compact & 2) != 0;
+  int host_threads = env_int("GEOT_B200_HOST_THREADS", 0);
+  if (host_threads <= 0) host_threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  int64_t max_rows = 0;   // rows of the widest slice: [first row of slice k (0 for k = 0), first row of slice k+1 (S at the end))
+  for (int k = 0; k < n_slices; ++k) {
+    const int64_t ra = (k == 0) ? 0 : dst_index[cut[k]], rb = (k + 1 < n_slices) ? dst_index[cut[k + 1]] : S;
+    max_rows = std::max(max_rows, rb - ra);
+  }
+  const size_t stage_rp = c_rows ? align256((size_t)(max_rows + 1) * 8) : 0;
+  const size_t stage_si = c_src32 ? align256((size_t)max_slice * 4) : 0;
+
   // double-buffered slice operands + src + dst + workspace
   const size_t slice_bytes = align256((size_t)max_slice * 8) * (gather ? 2 : 1) + align256((size_t)max_slice * wpe) +
-                             align256((size_t)max_slice * src_pe);
+                             align256((size_t)max_slice * src_pe) + stage_rp + stage_si;
   const size_t b_ws = geot_b200_workspace_bytes(max_slice, W, dtype, 1);
   const size_t total = align256(b_src) + align256(b_dst) + 2 * slice_bytes + align256(b_ws);
   Arena &a = g_arena;
@@ -645,6 +710,13 @@ int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t 
     HOST_TRY(cudaMalloc(&a.base, total));
     a.bytes = total;
   }
+  if (a.pinned_bytes < 2 * (stage_rp + stage_si)) {
+    if (a.pinned) HOST_TRY(cudaFreeHost(a.pinned));
+    a.pinned = nullptr; a.pinned_bytes = 0;
+    HOST_TRY(cudaHostAlloc(reinterpret_cast<void **>(&a.pinned), 2 * (stage_rp + stage_si), cudaHostAllocDefault));
+    a.pinned_bytes = 2 * (stage_rp + stage_si);
+  }
+  unsigned long long h2d_bytes = gather ? b_src : 0, d2h_bytes = 0;
   char *p = a.base;
   char *d_src = p; p += align256(b_src);
   char *d_dst = p; p += align256(b_dst);
@@ -663,23 +735,64 @@ int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t 
     int64_t *s_si = nullptr;
     if (gather) { s_si = reinterpret_cast<int64_t *>(q); q += align256((size_t)max_slice * 8); }
     char *s_w = q; q += align256((size_t)max_slice * wpe);
-    char *s_x = q;
+    char *s_x = q; q += align256((size_t)max_slice * src_pe);
+    int64_t *s_rp = reinterpret_cast<int64_t *>(q); q += stage_rp;          // compact transport: device staging
+    int32_t *s_si32 = reinterpret_cast<int32_t *>(q);
+    // rows [first row of slice k, first row of slice k+1) belong to this slice
+    const int64_t r0 = dst_index[e0], r1 = (k + 1 < n_slices) ? dst_index[cut[k + 1]] : S;
+    const int64_t rr0 = (k == 0) ? 0 : r0;
+    // compact transport: the host threads prepare slice k while slice k-1 is on the link.  The pinned staging
+    // half is free once the copies of slice k-2 have left it.
+    char *hp = a.pinned + (size_t)(k & 1) * (stage_rp + stage_si);
+    int64_t *h_rp = reinterpret_cast<int64_t *>(hp);
+    int32_t *h_si32 = reinterpret_cast<int32_t *>(hp + stage_rp);
+    if ((c_rows || c_src32) && k >= 2) HOST_TRY(cudaEventSynchronize(a.copied[k - 2]));
+    if (c_rows) host_row_pointers(dst_index + e0, n, rr0, r1 - rr0, h_rp, host_threads);
+    if (c_src32) {
+      const int64_t *si = src_index + e0;
+      parallel_ranges(host_threads, n, [=](int64_t b, int64_t e) { for (int64_t i = b; i < e; ++i) h_si32[i] = (int32_t)si[i]; });
+    }
     // the buffer is free once slice k-2 has been reduced
     if (k >= 2) HOST_TRY(cudaStreamWaitEvent(a.h2d, a.reduced[k - 2], 0));
-    HOST_TRY(cudaMemcpyAsync(s_di, dst_index + e0, (size_t)n * 8, cudaMemcpyHostToDevice, a.h2d));
-    if (gather) HOST_TRY(cudaMemcpyAsync(s_si, src_index + e0, (size_t)n * 8, cudaMemcpyHostToDevice, a.h2d));
+    if (c_rows) {
+      HOST_TRY(cudaMemcpyAsync(s_rp, h_rp, (size_t)(r1 - rr0 + 1) * 8, cudaMemcpyHostToDevice, a.h2d));
+      h2d_bytes += (size_t)(r1 - rr0 + 1) * 8;
+    } else {
+      HOST_TRY(cudaMemcpyAsync(s_di, dst_index + e0, (size_t)n * 8, cudaMemcpyHostToDevice, a.h2d));
+      h2d_bytes += (size_t)n * 8;
+    }
+    if (c_src32) {
+      HOST_TRY(cudaMemcpyAsync(s_si32, h_si32, (size_t)n * 4, cudaMemcpyHostToDevice, a.h2d));
+      h2d_bytes += (size_t)n * 4;
+    } else if (gather) {
+      HOST_TRY(cudaMemcpyAsync(s_si, src_index + e0, (size_t)n * 8, cudaMemcpyHostToDevice, a.h2d));
+      h2d_bytes += (size_t)n * 8;
+    }
     if (weight) HOST_TRY(cudaMemcpyAsync(s_w, static_cast<const char *>(weight) + (size_t)e0 * wpe, (size_t)n * wpe, cudaMemcpyHostToDevice, a.h2d));
     if (!gather) HOST_TRY(cudaMemcpyAsync(s_x, static_cast<const char *>(src) + (size_t)e0 * src_pe, (size_t)n * src_pe, cudaMemcpyHostToDevice, a.h2d));
+    h2d_bytes += (size_t)n * (wpe + src_pe);
     HOST_TRY(cudaEventRecord(a.copied[k], a.h2d));
     HOST_TRY(cudaStreamWaitEvent(a.comp, a.copied[k], 0));
-    rc = segment_reduce_impl(gather ? d_src : s_x, s_si, s_di, weight ? s_w : nullptr, d_dst, n, S, H, F, dtype, reduce,
-                             weight_layout, 1, nullptr, d_ws, b_ws, a.comp, /*clear_mode=*/1);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (c_rows) {   // expand the row pointer into slice-local dst ids [0, r1 - rr0)
+      csr_rows_kernel<int64_t><<<nb, 256, 0, a.comp>>>(s_rp, r1 - rr0, n, s_di);
+      HOST_TRY(cudaGetLastError());
+    }
+    if (c_src32) {
+      widen_index_kernel<<<nb, 256, 0, a.comp>>>(s_si32, s_si, n);
+      HOST_TRY(cudaGetLastError());
+    }
+    if (c_rows)     // slice-local dst ids: the slice's rows start at d_dst + rr0 * W
+      rc = segment_reduce_impl(gather ? d_src : s_x, s_si, s_di, weight ? s_w : nullptr, d_dst + (size_t)rr0 * W * es, n, r1 - rr0,
+                               H, F, dtype, reduce, weight_layout, 1, nullptr, d_ws, b_ws, a.comp, /*clear_mode=*/1);
+    else
+      rc = segment_reduce_impl(gather ? d_src : s_x, s_si, s_di, weight ? s_w : nullptr, d_dst, n, S, H, F, dtype, reduce,
+                               weight_layout, 1, nullptr, d_ws, b_ws, a.comp, /*clear_mode=*/1);
     if (rc != GEOT_OK) { cudaDeviceSynchronize(); return rc; }
     HOST_TRY(cudaEventRecord(a.reduced[k], a.comp));
-    // rows [first row of slice k, first row of slice k+1) are final: send them home
-    const int64_t r0 = dst_index[e0], r1 = (k + 1 < n_slices) ? dst_index[cut[k + 1]] : S;
+    // rows [rr0, r1) are final: send them home
     HOST_TRY(cudaStreamWaitEvent(a.d2h, a.reduced[k], 0));
-    const int64_t rr0 = (k == 0) ? 0 : r0;
+    d2h_bytes += (size_t)(r1 - rr0) * W * es;
     HOST_TRY(cudaMemcpyAsync(static_cast<char *>(dst) + (size_t)rr0 * W * es, d_dst + (size_t)rr0 * W * es,
                              (size_t)(r1 - rr0) * W * es, cudaMemcpyDeviceToHost, a.d2h));
   }
@@ -687,7 +800,22 @@ int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const int64_t 
   HOST_TRY(cudaStreamSynchronize(a.comp));
   HOST_TRY(cudaStreamSynchronize(a.h2d));
 #undef HOST_TRY
+  a.last_h2d = h2d_bytes;
+  a.last_d2h = d2h_bytes;
   return rc;
+}
+
+int geot_b200_host_row_pointers(const int64_t *index, int64_t n, int64_t row0, int64_t rows, int64_t *rowptr, int threads) {
+  if (!index || !rowptr || n < 0 || rows < 0) return GEOT_ERR_INVALID_ARG;
+  if (threads <= 0) threads = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  host_row_pointers(index, n, row0, rows, rowptr, threads);
+  return GEOT_OK;
+}
+
+int geot_b200_host_last_transfer(unsigned long long *h2d_bytes, unsigned long long *d2h_bytes) {
+  if (h2d_bytes) *h2d_bytes = g_arena.last_h2d;
+  if (d2h_bytes) *d2h_bytes = g_arena.last_d2h;
+  return GEOT_OK;
 }
 
 }  // extern "C"

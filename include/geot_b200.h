@@ -222,6 +222,22 @@ GEOT_API int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const
                                   int weight_layout);
 GEOT_API int geot_b200_host_arena_release(void);
 
+/* Compact transport of the host-buffer entry (environment GEOT_B200_HOST_COMPACT, bit mask, default 0 = off):
+ *   1: each slice sends its CSR row pointer (rows + 1 values, computed by the host threads below) instead of its
+ *      dst_index (one value per edge); the device expands it (the inverse of geot::coo_to_csr);
+ *   2: src_index travels as int32 (narrowed by the host threads, widened on the device; N_src < 2^31).
+ * Results are identical; the bytes over the link drop (Reddit-shape gather_weight_scatter: 2.41 -> 1.49 -> 1.04 GB).
+ * GEOT_B200_HOST_THREADS bounds the host threads (default: hardware concurrency, at most 32).
+ * geot_b200_host_last_transfer reports the bytes the last host call really moved in each direction. */
+GEOT_API int geot_b200_host_last_transfer(unsigned long long *h2d_bytes, unsigned long long *d2h_bytes);
+
+/* Host-side CSR row pointer of a sorted index slice (pure CPU, no CUDA call):
+ *     rowptr[i] = first position p in index[0, n) with index[p] >= row0 + i,      i = 0 .. rows
+ * == geot::coo_to_csr (geot/match_replace/format_transform.py:5-18) for row0 = 0, rows = index[n-1] + 1, and the
+ * segment-pointer pass of the reference's CPU kernel (csrc/cpu/index_scatter_cpu.cpp:36-75).  threads <= 0: all. */
+GEOT_API int geot_b200_host_row_pointers(const int64_t *index, int64_t n, int64_t row0, int64_t rows, int64_t *rowptr,
+                                int threads);
+
 /* ---- instrumentation -------------------------------------------------------------------------- */
 
 /* geot_b200_profile_enable(n > 0): every following segment-reduce call on this host thread records a

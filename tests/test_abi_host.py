@@ -116,3 +116,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "geot_oracle" not in text, f
+
+
+@pytest.mark.parametrize("threads", [1, 3, 16])
+def test_host_row_pointers_match_the_oracle(threads):
+    """The host-side segment-pointer pass of the compact transport (pure CPU code of the library): bit-exact against
+    the oracle's rowptr (= coo_to_csr) on whole indices and on slices, with gaps, hubs and single-edge rows."""
+    import oracle
+    from geot_b200 import abi
+    g = torch.Generator().manual_seed(threads)
+    for (E, N, skew) in [(1, 1, 1), (50, 400, 1), (20000, 300, 3), (200000, 50000, 2), (300000, 7, 1)]:
+        w = torch.rand(N, generator=g) ** skew
+        di = torch.multinomial(w / w.sum(), E, replacement=True, generator=g).sort().values.contiguous()
+        S = int(di[-1]) + 1
+        exp = oracle.rowptr(di, S)
+        assert torch.equal(abi.host_row_pointers(di, 0, S, threads), exp)
+        assert torch.equal(abi.host_row_pointers(di, 0, S + 9, threads)[S:], torch.full((10,), E))     # trailing empty rows
+        # a slice cut at a segment boundary, rows relative to its first row (what the host entry sends per slice)
+        e0 = int(exp[S // 2])
+        r0 = S // 2
+        sl = di[e0:].contiguous()
+        got = abi.host_row_pointers(sl, r0, S - r0, threads)
+        assert torch.equal(got, exp[r0:] - e0)

@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round-2 single-GPU session.  Build the tuning variant HERE first (it travels with the snapshot):
+#   make -f geot_b200/csrc/Makefile VARIANT=_u4 EXTRA="-DGEOT_U0=4" -j8 lib
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_r02_single.sh [tag]'
+# Legs (each writes its own file as soon as it ends):
+#  1. parity tests (the whole -m gpu suite: includes the exchange kernels, push_rows, compact host transport)
+#  2. bench own arm with each host transport (e2e: 0 plain, 1 row pointers, 3 row pointers + int32 src ids)
+#  3. bf16 max/min register-path kernels: U0 = 8 (spills) against the U0 = 4 variant (spill-free)
+#  4. L2 capacity probe: Reddit gws at F = 32 / 64 / 128 (src 30 / 60 / 119 MB) with ncu hit rates
+#  5. ncu full capture of the lean depth-7 index_scatter kernel
+TAG=${1:-r02}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem --format=csv > $OUT/gpu.txt 2>&1
+echo "== pytest -m gpu"; timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
+for m in 0 1 3; do
+  echo "== bench, host transport $m"
+  GEOT_B200_HOST_COMPACT=$m timeout 600 python bench.py --steps 20 --warmup 5 2>$OUT/bench_compact$m.err | tail -1 | tee $OUT/bench_compact$m.json
+done
+echo "== bf16 max: U0 = 8 (default library) vs U0 = 4 (variant)"
+for lib in default geot_b200/lib/libgeot_b200_u4.so; do
+  [ "$lib" = default ] || export GEOT_B200_LIB=$PWD/$lib
+  timeout 300 python scripts/bench_reduce_ops.py 2>&1 | sed "s|^|lib=$lib |" | tee -a $OUT/bf16_u0.txt
+done
+unset GEOT_B200_LIB
+echo "== L2 capacity probe"
+for F in 32 64 128; do
+  timeout 600 ncu --metrics lts__t_sector_hit_rate.pct,dram__bytes_read.sum,gpu__time_duration.sum --clock-control none \
+      -k regex:segment_reduce_kernel -s 4 -c 1 --csv --log-file $OUT/l2probe_F$F.csv python scripts/l2_probe.py $F > $OUT/l2probe_F$F.log 2>&1
+done
+echo "== ncu full capture: reddit index_scatter (lean ring depth 7)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:segment_reduce_kernel -s 3 -c 1 -o $OUT/prof_reddit_index_scatter \
+    python bench.py --workload reddit_index_scatter --steps 3 --warmup 3 > $OUT/prof_reddit_index_scatter.log 2>&1
+ls -la $OUT

@@ -307,7 +307,18 @@ def run_own(args):
         del ws
         ws = None
 
+    # opt-in experiment (N = 1, gather ops, one weight per edge at most): temporal blocking of the src matrix for L2
+    blocked, w_blocked = None, None
+    n_blocks = int(os.environ.get("GEOT_B200_SRC_BLOCKS", "0"))
+    if n_blocks > 1 and world == 1 and wk["op"] != "index_scatter" and H == 1:
+        blocked = gdist.SrcBlockedGather(l_si, l_di, l_S, N, n_blocks)
+        w_blocked = blocked.permute_weight(l_w) if l_w is not None else None      # static weights: permuted once
+        calls_per_step = n_blocks
+
     def step():
+        if blocked is not None:
+            blocked(wk["x"], w_blocked, "sum", out=out, permuted=True)
+            return
         if pg is not None:
             pg(x_full, l_w, "sum", out=out)
             return
@@ -443,6 +454,9 @@ def run_own(args):
     }
     if l2_note:
         line["config"]["l2_persist"] = l2_note
+    if blocked is not None:
+        line["config"]["src_blocks"] = n_blocks
+        line["gpu_launches"] = (2 * n_blocks + 1) * args.steps
     if exchanged is not None:
         line["config"]["src_rows_received_per_step_rank0"] = exchanged[0]
         line["config"]["src_rows_full_exchange_rank0"] = exchanged[1]

@@ -552,3 +552,51 @@ class PeerPushGather(PipelinedGather):
         self._combine(parts, out, reduce)
         return out
 
+
+class SrcBlockedGather(PipelinedGather):
+    """Single-GPU experiment: temporal blocking of the src matrix for L2.  The edges are split stably into ``blocks``
+    buckets by src row range (each still dst-sorted) and reduced one bucket after the other, so that at any time the
+    gathers touch ``1/blocks`` of the src matrix; the bucket partials are combined in bucket order.  Pays only when
+    the saved DRAM re-reads exceed the partial-sum traffic (``2*blocks + 1`` passes over the output): high-degree
+    graphs whose src matrix is a small multiple of the L2 (Reddit-shape: 119 MB src, degree 492), not products-like
+    ones.  Same kernels, same plans per bucket, no communication."""
+
+    def __init__(self, src_index: torch.Tensor, dst_index: torch.Tensor, num_dst_rows: int, num_src_rows: int,
+                 blocks: int, reducer=None, combiner=None, permuter=None):
+        E = dst_index.numel()
+        self.shard = GraphShard(0, 1, [0, num_dst_rows], [0, E], src_index, dst_index, None)
+        self.group, self.world, self.rank = None, 1, 0
+        self.cuda = dst_index.is_cuda
+        self._reducer, self._combiner, self._permuter = reducer, combiner, permuter
+        self._plans, self._ws, self._parts, self._wperm = {}, None, None, None
+        self._rowptr, self.needed = None, None
+        self.blocks = blocks
+        rows_per_block = (num_src_rows + blocks - 1) // blocks
+        key = torch.div(src_index, rows_per_block, rounding_mode="floor")
+        perm = torch.argsort(key, stable=True)
+        counts = torch.bincount(key, minlength=blocks).tolist()
+        bounds = [0]
+        for c in counts:
+            bounds.append(bounds[-1] + int(c))
+        self.buckets = SrcBuckets(perm, bounds, src_index[perm].contiguous(), dst_index[perm].contiguous())
+
+    def permute_weight(self, weight: torch.Tensor) -> torch.Tensor:
+        """Per-edge weights in bucket order (a copy): pass it with ``permuted=True`` when the weights are static."""
+        return self._permute(weight).clone()
+
+    def __call__(self, x: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum",
+                 out: Optional[torch.Tensor] = None, permuted: bool = False) -> torch.Tensor:
+        assert reduce in ("sum", "mean"), "bucket partials are combined by addition: sum / mean only"
+        S = self.shard.num_local_rows
+        tail = list(x.shape[1:])
+        if out is None:
+            out = x.new_empty([S] + tail)
+        if self._parts is None or list(self._parts.shape[2:]) != tail or self._parts.dtype != x.dtype:
+            self._parts = x.new_empty([self.blocks, S] + tail)
+        w_all = None if weight is None else (weight if permuted else self._permute(weight))
+        b = self.buckets.bounds
+        for k in range(self.blocks):
+            self._reduce_bucket(k, x, w_all[b[k]:b[k + 1]] if w_all is not None else None, self._parts[k])
+        self._combine(self._parts, out, reduce)
+        return out
+

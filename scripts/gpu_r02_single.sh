@@ -7,7 +7,8 @@
 #  2. bench own arm with each host transport (e2e: 0 plain, 1 row pointers, 3 row pointers + int32 src ids)
 #  3. bf16 max/min register-path kernels: U0 = 8 (spills) against the U0 = 4 variant (spill-free)
 #  4. L2 capacity probe: Reddit gws at F = 32 / 64 / 128 (src 30 / 60 / 119 MB) with ncu hit rates
-#  5. ncu full capture of the lean depth-7 index_scatter kernel
+#  5. src blocking A/B (GEOT_B200_SRC_BLOCKS = 2 / 3 / 4)
+#  6. ncu full capture of the lean depth-7 index_scatter kernel
 TAG=${1:-r02}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -27,6 +28,13 @@ echo "== L2 capacity probe"
 for F in 32 64 128; do
   timeout 600 ncu --metrics lts__t_sector_hit_rate.pct,dram__bytes_read.sum,gpu__time_duration.sum --clock-control none \
       -k regex:segment_reduce_kernel -s 4 -c 1 --csv --log-file $OUT/l2probe_F$F.csv python scripts/l2_probe.py $F > $OUT/l2probe_F$F.log 2>&1
+done
+echo "== src blocking (temporal L2 blocking of the src matrix) on the Reddit and proteins shapes"
+for wl in reddit_gws proteins_gws256; do
+  for b in 2 3 4; do
+    GEOT_B200_SRC_BLOCKS=$b timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 2>$OUT/blocks_${wl}_$b.err | tail -1 > $OUT/blocks_${wl}_$b.json
+    python -c "import json,sys; d=json.load(open('$OUT/blocks_${wl}_$b.json')); print('$wl blocks=$b', d['ms_per_step'], 'ms', d['value'], 'GB/s')" | tee -a $OUT/blocks.txt
+  done
 done
 echo "== ncu full capture: reddit index_scatter (lean ring depth 7)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:segment_reduce_kernel -s 3 -c 1 -o $OUT/prof_reddit_index_scatter \

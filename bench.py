@@ -287,8 +287,6 @@ def run_own(args):
     # with the reduction of per-owner edge buckets (geot_b200.dist.PipelinedGather); "allgather": one NCCL all-gather,
     # then one reduction.  Both are inside the timed region.
     exchange = os.environ.get("GEOT_B200_EXCHANGE", "pipeline") if (world > 1 and wk["op"] != "index_scatter") else "none"
-    if exchange in ("pipeline", "needed", "push") and H > 1:
-        exchange = "allgather"          # per-head weights: not regrouped by the pipelined path yet
     if exchange not in ("pipeline", "needed", "push", "allgather", "replicated", "none"):
         raise SystemExit("GEOT_B200_EXCHANGE must be pipeline, needed, push, allgather or replicated")
     calls_per_step = 1

@@ -252,6 +252,7 @@ def build_needed_rows(shard: GraphShard, buckets: SrcBuckets, group=None) -> Nee
 class PipelinedGather:
     """``gather_(weight_)scatter`` on a dst-row shard with the src-row exchange overlapped (sum / mean).
 
+    Rows may be ``[N, F]`` (weights ``[E]`` or none) or ``[N, H, F]`` with per-head weights ``[E, H]`` (``mh_spmm``).
     ``x_full`` is the caller's [N, ...] replica buffer whose OWN row range already holds this rank's rows (the
     producer writes them there; ``local_rows(x_full)`` is that view).  Every call exchanges the other ranks' rows
     into it while reducing.  ``reducer`` / ``combiner`` / ``permuter`` default to the C-ABI kernels; the gloo tests
@@ -299,7 +300,8 @@ class PipelinedGather:
             sizes = [self.buckets.bounds[i + 1] - self.buckets.bounds[i] for i in range(len(self.buckets.bounds) - 1)]
             need = lambda n: abi.lib().geot_b200_workspace_bytes(n, W, abi.DTYPE[x_full.dtype], 1)
             self._ws = abi.Workspace(max(sizes, key=need), W, x_full.dtype, x_full.device)
-        abi.segment_reduce(x_full, si, di, w_b, "sum", S=S, plan=self._plans[k], out=out, workspace=self._ws)
+        H = x_full.shape[1] if x_full.dim() == 3 else 1        # [N, H, F] rows with [E, H] weights: mh_spmm
+        abi.segment_reduce(x_full, si, di, w_b, "sum", S=S, H=H, plan=self._plans[k], out=out, workspace=self._ws)
 
     def _combine(self, parts, out, reduce):
         if self._combiner is not None:

@@ -72,7 +72,7 @@ def _worker(rank, world, port, q, hub=False):
     # (oracle as the checker) for the three device kernels; the host logic under test is the bucketing, the step
     # schedule and the bucket order.
     def reducer(xf, si, di, w, S):
-        return oracle.segment_reduce(xf, si, di, w, "sum", S=S)
+        return oracle.segment_reduce(xf, si, di, w, "sum", S=S, H=(xf.shape[1] if xf.dim() == 3 else 1))
 
     def combiner(parts, reduce, dst_local, S):
         tot = parts.sum(0)
@@ -175,6 +175,21 @@ def _worker(rank, world, port, q, hub=False):
             full = (oracle.gather_weight_scatter(src_index, dst, weight, x, reduce) if wt is not None
                     else oracle.gather_scatter(src_index, dst, x, reduce))
             assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), ("push", reduce)
+
+    # multi-head rows [N, H, F] with per-head weights [E, H] (mh_spmm) through all three overlapped forms
+    Hh = 3
+    xh = torch.rand(N, Hh, 4, generator=g)
+    wh = torch.rand(E, Hh, generator=g)
+    sh_h = gdist.shard_graph(src_index, dst, wh, rank, world, row_bounds=rb, edge_bounds=eb)
+    exp_h = oracle.mh_spmm(src_index, dst, wh, xh)[rb[rank]:rb[rank + 1]]
+    xh_local = xh[rb[rank]:rb[rank + 1]].clone()
+    for make in (lambda: gdist.PipelinedGather(sh_h, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm]),
+                 lambda: gdist.PipelinedGather(sh_h, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm],
+                                               needed_only=True),
+                 lambda: gdist.PeerPushGather(sh_h, **kw_push)):
+        obj = holder["pp"] = make()
+        got = obj.aggregate(xh_local, sh_h.weight, "sum")
+        assert torch.allclose(got, exp_h, rtol=1e-5, atol=1e-6), type(obj).__name__
 
     # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): every layer through the pipelined
     # exchange (both forms), against the plain-torch restatement of the stack on the unsharded graph

@@ -77,6 +77,18 @@ def _worker(rank, world, port, q):
                     assert torch.equal(c1, c2), "peer-push result is not bit-reproducible"
                     bad = (c1.cpu().double() - exp).abs() > tol * exp.abs().clamp_min(1e-3 if dtype != torch.float32 else 1e-30)
                     assert not bad.any(), ("push", F, dtype, reduce, weighted, int(bad.sum()))
+    # multi-head rows with per-head weights (mh_spmm, BASELINE configs[3] shape class) through the overlapped forms
+    Hh, Fh = 8, 32
+    xh = torch.rand(N, Hh, Fh, generator=g).bfloat16()
+    wh = torch.rand(E, Hh, generator=g).bfloat16()
+    sh_h = gdist.shard_graph(dense.to(dev), dst.to(dev), wh.to(dev), rank, world)
+    rbh = sh_h.row_bounds
+    exp_h = oracle.mh_spmm(dense, dst, wh, xh)[rbh[rank]:rbh[rank + 1]].double()
+    xh_local = xh[rbh[rank]:rbh[rank + 1]].to(dev)
+    for obj in (gdist.PipelinedGather(sh_h), gdist.PipelinedGather(sh_h, needed_only=True), gdist.PeerPushGather(sh_h)):
+        got = obj.aggregate(xh_local, sh_h.weight, "sum").cpu().double()
+        assert not ((got - exp_h).abs() > 2e-2 * exp_h.abs().clamp_min(1e-3)).any(), type(obj).__name__
+
     # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): all three exchange forms against
     # the single-GPU forward of the same stack on the unsharded graph
     from geot_b200 import gnn

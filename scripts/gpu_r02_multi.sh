@@ -33,5 +33,9 @@ run reddit_gws_needed GEOT_B200_EXCHANGE=needed -- --steps 10 --warmup 3
 run reddit_gws_allgather GEOT_B200_EXCHANGE=allgather -- --steps 10 --warmup 3
 run reddit_gws_replicated GEOT_B200_EXCHANGE=replicated -- --steps 10 --warmup 3
 run reddit_index_scatter X=1 -- --workload reddit_index_scatter --steps 5 --warmup 3
+echo "== 3-layer GCN / GraphSAGE forward on the shards (configs[4])"
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
+    scripts/bench_model_multi.py > $OUT/model.jsonl 2> $OUT/model.err
+cat $OUT/model.jsonl | cut -c1-900; tail -3 $OUT/model.err
 date +%s > $OUT/t1
 ls -la $OUT

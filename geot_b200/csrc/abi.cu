@@ -226,6 +226,32 @@ __global__ void csr_rows_kernel(const P *__restrict__ rowptr, int64_t S, int64_t
   row[e] = lo;
 }
 
+// Rows that receive no edge must read 0.  With a plan the empty rows are known (rowptr[r+1] == rowptr[r], and every
+// row at or beyond the plan's S): a warp checks 32 rows, then zero-fills the empty ones cooperatively -- the writes
+// are the empty rows only instead of a memset of the whole dst (arxiv-shape mh_spmm: 87 MB per call).
+__global__ void __launch_bounds__(256)
+zero_empty_rows_kernel(const int64_t *__restrict__ rowptr, int64_t plan_rows, int64_t S, int64_t row_bytes, char *dst, int vec16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp * 32; base < S; base += n_warps * 32) {
+    const int64_t r = base + lane;
+    bool empty = false;
+    if (r < S) empty = (r >= plan_rows) || (rowptr[r + 1] == rowptr[r]);
+    unsigned m = __ballot_sync(0xffffffffu, empty);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      char *row = dst + (base + b) * row_bytes;
+      if (vec16) {
+        for (int64_t o = (int64_t)lane * 16; o < row_bytes; o += 32 * 16) *reinterpret_cast<uint4 *>(row + o) = make_uint4(0, 0, 0, 0);
+      } else {
+        for (int64_t o = (int64_t)lane * 2; o < row_bytes; o += 32 * 2) *reinterpret_cast<unsigned short *>(row + o) = 0;
+      }
+    }
+  }
+}
+
 // int32 -> int64 (compact host transport of src_index, geot_b200_segment_reduce_host)
 __global__ void widen_index_kernel(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,7 +482,18 @@ int segment_reduce_impl(const void *src, const int64_t *src_index, const int64_t
   // Rows that receive no edge must read 0.  The kernels store every non-empty row exactly once and
   // never touch the others, so dst is cleared first unless the plan proves there is no empty row.
   const bool need_clear = clear_mode == 0 && !(plan && !plan->has_gaps && plan->S == S);
-  if (need_clear) CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)S * (size_t)W * dtype_size(dtype), stream));
+  if (need_clear) {
+    // GEOT_B200_ZERO_EMPTY=1 (off until measured): with a plan, zero only the rows it proves empty
+    const size_t row_bytes = (size_t)W * dtype_size(dtype);
+    if (plan && plan->is_sorted && plan->rowptr && env_int("GEOT_B200_ZERO_EMPTY", 0) == 1) {
+      const int vec16 = (row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? 1 : 0;
+      const unsigned nb = (unsigned)std::min<int64_t>((S + 255) / 256, 148 * 8);
+      zero_empty_rows_kernel<<<nb, 256, 0, stream>>>(plan->rowptr, plan->S, S, (int64_t)row_bytes, static_cast<char *>(dst), vec16);
+      CUDA_TRY(cudaGetLastError());
+    } else {
+      CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)S * row_bytes, stream));
+    }
+  }
 
   geot::Params p;
   p.src = src;

@@ -24,6 +24,10 @@ for lib in default geot_b200/lib/libgeot_b200_u4.so; do
   timeout 300 python scripts/bench_reduce_ops.py 2>&1 | sed "s|^|lib=$lib |" | tee -a $OUT/bf16_u0.txt
 done
 unset GEOT_B200_LIB
+echo "== zero only the empty rows (GEOT_B200_ZERO_EMPTY) on the workload with gaps"
+for z in 0 1; do
+  GEOT_B200_ZERO_EMPTY=$z timeout 300 python scripts/tune.py arxiv_mh_spmm 0 2>&1 | grep -E "lib=|rror" | sed "s/^/zero_empty=$z /" | tee -a $OUT/zero_empty.txt
+done
 echo "== L2 capacity probe"
 for F in 32 64 128; do
   timeout 600 ncu --metrics lts__t_sector_hit_rate.pct,dram__bytes_read.sum,gpu__time_duration.sum --clock-control none \

@@ -139,3 +139,30 @@ def test_host_entry_compact_transport(monkeypatch, mask):
             if (mask & 1) or s_i is not None:
                 assert h2d < moved[i][0], (mask, i, h2d, moved[i][0])
     assert abi.lib().geot_b200_host_arena_release() == 0
+
+
+@pytest.mark.parametrize("dtype,F", [(torch.float32, 64), (torch.float32, 7), (torch.bfloat16, 24), (torch.float64, 3)])
+def test_zero_only_the_empty_rows(monkeypatch, dtype, F):
+    """GEOT_B200_ZERO_EMPTY=1: with a plan, rows without edges are zero-filled one by one instead of a memset of the
+    whole output.  Same result bit for bit, on a graph with runs of empty rows, a dirty output buffer and S beyond the
+    plan's last row."""
+    g = torch.Generator().manual_seed(F)
+    N, E = 3000, 20000
+    wdeg = torch.rand(N, generator=g) ** 3
+    wdeg[100:400] = 0                                            # a run of empty rows
+    wdeg[::7] = 0                                                # scattered empty rows
+    di = torch.multinomial(wdeg / wdeg.sum(), E, replacement=True, generator=g).sort().values.to(DEV)
+    si = torch.randint(0, N, (E,), generator=g).to(DEV)
+    x = torch.rand(N, F, generator=g).to(dtype).to(DEV)
+    plan = abi.DevicePlan(di)
+    assert plan.c.has_gaps == 1
+    for S in (plan.S, plan.S + 37):
+        outs = []
+        for flag in ("0", "1"):
+            monkeypatch.setenv("GEOT_B200_ZERO_EMPTY", flag)
+            out = torch.full((S, F), 7.0, dtype=dtype, device=DEV)           # dirty: stale values must not survive
+            abi.segment_reduce(x, si, di, None, "sum", S=S, plan=plan, out=out)
+            outs.append(out.clone())
+        assert torch.equal(outs[0], outs[1])
+        deg = torch.bincount(di.cpu(), minlength=S)
+        assert bool((outs[1].cpu()[deg == 0] == 0).all())

@@ -28,6 +28,10 @@ echo "== zero only the empty rows (GEOT_B200_ZERO_EMPTY) on the workload with ga
 for z in 0 1; do
   GEOT_B200_ZERO_EMPTY=$z timeout 300 python scripts/tune.py arxiv_mh_spmm 0 2>&1 | grep -E "lib=|rror" | sed "s/^/zero_empty=$z /" | tee -a $OUT/zero_empty.txt
 done
+echo "== chunk sweep on the two small (latency-bound) workloads"
+for wl in arxiv_mh_spmm config1_index_scatter; do
+  timeout 300 python scripts/tune.py $wl 0,16,32,64,128,256 2>&1 | grep -E "lib=|rror" | tee -a $OUT/chunk_sweep_small.txt
+done
 echo "== L2 capacity probe"
 for F in 32 64 128; do
   timeout 600 ncu --metrics lts__t_sector_hit_rate.pct,dram__bytes_read.sum,gpu__time_duration.sum --clock-control none \

@@ -152,19 +152,26 @@ constexpr int kTmaFlag = 16;
 //            instructions per 512-byte row instead of 32 (profiles/r01c_*).  sum kernels with fp32 accumulators,
 //            no per-head weights, chunks that are whole batches.
 constexpr int kLeanFlag = 32;
+//   PF & 64 (kDirectFlag, with kLeanFlag; experiment, GEOT_B200_RING=96): the LEAN REGISTER path -- the lean
+//            bookkeeping (ids / weights parked in shared memory, position-based run lengths) with the rows loaded
+//            straight into two register buffers of U rows (one consumed while the next is in flight), so a gathered
+//            byte crosses the L1TEX data pipe once instead of twice (LDGSTS in + LDS out: 84 % busy on Reddit gws).
+constexpr int kDirectFlag = 64;
 template <typename T, int VECW, int LPR, int VPL, int PF_>
 struct ShapeOf {
   using A = typename AccOf<T>::type;
   static constexpr bool TMA = (PF_ & kTmaFlag) != 0;
-  static constexpr bool LEAN = (PF_ & kLeanFlag) != 0;
-  static constexpr int PF = PF_ & (kTmaFlag - 1);   // ring depth
+  static constexpr bool DIRECT = (PF_ & kDirectFlag) != 0;
+  static constexpr bool LEAN = (PF_ & kLeanFlag) != 0 && !DIRECT;   // the lean RING
+  static constexpr int PF = DIRECT ? 0 : (PF_ & (kTmaFlag - 1));   // ring depth
   static constexpr int NG = kThreads / LPR;      // chunks (groups) per tile
   static constexpr int CW = LPR * VPL * VECW;    // columns per CTA
   // ring: 4 rows per sub-batch (2 for the widest rows) measured best on B200 (profiles/r01_ring_sweep.md)
   static constexpr int RU = GEOT_RING_U > 0 ? (GEOT_RING_U / VPL > 0 ? GEOT_RING_U / VPL : 1) : (VPL >= 4 ? 2 : 4);
   // lean ring: 2 KB of rows per warp and stage, at least 4 sub-batches per batch
   static constexpr int LU = (VPL >= 4) ? 1 : (VPL == 2 ? 2 : (LPR >= 16 ? 4 : (LPR >= 8 ? 2 : 1)));
-  static constexpr int U0 = LEAN ? LU : (PF > 0 ? RU : ((VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0)));
+  static constexpr int DU = (VPL >= 2) ? 4 : 8;   // lean register path: two buffers of DU rows = 64 data registers
+  static constexpr int U0 = DIRECT ? DU : (LEAN ? LU : (PF > 0 ? RU : ((VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0))));
   static constexpr int U = (LPR < U0) ? LPR : U0;   // rows per sub-batch
   static constexpr int NS = PF + 1;              // ring stages
   static constexpr int SB = LPR / U;             // sub-batches per batch
@@ -173,14 +180,16 @@ struct ShapeOf {
   static constexpr size_t scalars_off = (LEAN ? 1 : 2) * (size_t)NG * CW * sizeof(A);
   static constexpr size_t carry_bytes = ((scalars_off + (size_t)NG * (4 * 8 + 4)) + 127) & ~(size_t)127;
   // lean: per group two operand buffers of LPR src row ids + LPR weights
-  static constexpr size_t ops_bytes = LEAN ? (size_t)NG * 4 * LPR * 4 : 0;
+  static constexpr size_t ops_bytes = (LEAN || DIRECT) ? (size_t)NG * 4 * LPR * 4 : 0;
   static constexpr size_t ring_off = carry_bytes + ops_bytes;
   static constexpr size_t ring_bytes = PF > 0 ? (size_t)NG * NS * U * CW * sizeof(T) : 0;
   static constexpr size_t bar_bytes = TMA ? (((size_t)NG * NS * 8 + 127) & ~(size_t)127) : 0;   // one mbarrier per (group, stage)
   static constexpr size_t smem_bytes = ring_off + ring_bytes + bar_bytes;
   static constexpr int max_blocks = (int)((227 * 1024) / (smem_bytes + 1024));
   static constexpr int min_blocks_direct = (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1));
-  static constexpr int min_blocks = PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1));
+  static constexpr int min_blocks = DIRECT ? 2 : (PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1)));
+  static_assert(!DIRECT || (VPL <= 2 && SB % 2 == 0 && sizeof(A) == 4 && VECW * sizeof(T) == 16),
+                "lean register path: an even number of sub-batches per batch, fp32 accumulators, 16-byte vectors");
   static_assert(PF == 0 || LEAN || PF * U <= LPR, "the prefetch distance must stay within one batch ahead");
   static_assert(!LEAN || (PF > 0 && SB % NS == 0 && sizeof(A) == 4 && U * sizeof(T) >= sizeof(A)),
                 "lean ring: the stages must divide the batch; fp32 accumulators; a stage holds a carry row");
@@ -229,12 +238,13 @@ segment_reduce_kernel(const Params p) {
   constexpr int PF = SH::PF;
   constexpr bool TMA = SH::TMA;
   constexpr bool LEAN = SH::LEAN;
+  constexpr bool DIRECT = SH::DIRECT;
   constexpr int NG = SH::NG;      // chunks per tile
   constexpr int CW = SH::CW;      // columns per CTA
   constexpr int U = SH::U;        // row loads in flight per group (PF == 0) / rows per ring sub-batch
   constexpr int NS = SH::NS;
   static_assert(PF == 0 || VECW * sizeof(T) == 16, "the ring moves 16-byte pieces");
-  static_assert(!LEAN || (RED == RED_SUM && WM != WM_GENERIC), "lean ring: sum, at most one weight per edge");
+  static_assert(!(LEAN || DIRECT) || (RED == RED_SUM && WM != WM_GENERIC), "lean paths: sum, at most one weight per edge");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A *s_head = reinterpret_cast<A *>(smem_raw);              // [NG][CW]
@@ -378,7 +388,146 @@ segment_reduce_kernel(const Params p) {
         }
     };
 
-    if constexpr (LEAN) {
+    if constexpr (DIRECT) {
+      // ---- lean register path (see ShapeOf; experiment) ----------------------------------------------------
+      constexpr int SB = SH::SB;                   // sub-batches per batch (even)
+      constexpr int RING_WORDS = 2 * LPR;          // operand buffers: two batches, circular
+      const int n_edges = (int)(e_end - e_begin);
+      const int nfull = n_edges / LPR;             // whole batches; a remainder only in the edge list's last chunk
+      const int n_ring = nfull * LPR;              // edges that take the batched path
+      uint32_t *ids = reinterpret_cast<uint32_t *>(smem_raw + SH::carry_bytes) + g * (2 * RING_WORDS);   // src row ids
+      float *wts = reinterpret_cast<float *>(ids + RING_WORDS);                                          // weights
+      const uint32_t row_bytes32 = (uint32_t)p.W * (uint32_t)sizeof(T);
+      uint32_t ld32 = (uint32_t)last_dst;          // dst row of the edge left of the current batch
+
+      auto ld_ops = [&](int bi, uint32_t &d, uint32_t &sid, float &wv) {
+        const int64_t e = e_begin + (int64_t)bi * LPR + gl;
+        d = (uint32_t)ld_stream(dst_index + e, pol);
+        sid = src_index ? (uint32_t)ld_stream(src_index + e, pol) : (uint32_t)e;
+        wv = 1.f;
+        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + e, pol));
+      };
+      // loads the U rows whose ids are at o[0..U) into a register buffer (L2-only caching, like the ring's cp.async.cg)
+      auto fetch = [&](const uint32_t *o, VecT(&v)[U][VPL]) {
+        const Vec<uint32_t, U> r = *reinterpret_cast<const Vec<uint32_t, U> *>(o);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int j = 0; j < VPL; ++j) {
+            const uint4 t = __ldcg(reinterpret_cast<const uint4 *>(row_addr(lane_src[j], r.v[u], row_bytes32)));
+            v[u][j] = *reinterpret_cast<const VecT *>(&t);
+          }
+        }
+      };
+      auto add_edge = [&](const VecT(&v)[VPL], float we) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+#pragma unroll
+          for (int i = 0; i < VECW; ++i) {
+            float x = to_acc<T>(v[j].v[i]);
+            if (WM != WM_NONE) x = x * we;
+            acc[j][i] = acc[j][i] + x;
+          }
+      };
+
+      uint32_t d_cur = 0, d_nxt = 0, l_d = 0, l_s = 0;
+      float l_w = 1.f;
+      if (nfull > 0) {
+        ld_ops(0, d_cur, l_s, l_w);
+        ids[gl] = l_s;
+        wts[gl] = l_w;
+      }
+      if (nfull > 1) {
+        ld_ops(1, d_nxt, l_s, l_w);
+        ids[LPR + gl] = l_s;
+        wts[LPR + gl] = l_w;
+      }
+      __syncwarp(gmask);
+      VecT va[U][VPL], vb[U][VPL];                 // the sub-batch being consumed / the one in flight
+      if (nfull > 0) fetch(ids, va);
+      int pos = 0;          // chunk-relative position of the current pair of sub-batches
+      int run_start = 0;    // chunk-relative position where the open run began
+      int slot = 0;         // word offset of the current batch in the operand buffers: 0 or LPR
+      unsigned bmask = 0;
+      uint32_t batch_left = 0;
+      int batch_pos = 0;
+
+      // consumes sub-batch `t` (0 or 1) of the current pair from `v`, after putting the next one in flight into `vn`
+      auto step = [&](int t, int blk, VecT(&v)[U][VPL], VecT(&vn)[U][VPL]) {
+        const int c = (t + 1) * U;                                     // distance of the next sub-batch from `pos`
+        if (pos + c < n_ring) fetch(ids + ((blk + c) & (RING_WORDS - 1)), vn);
+        Vec<float, U> wv;
+#pragma unroll
+        for (int u = 0; u < U; ++u) wv.v[u] = 1.f;
+        if (WM == WM_EDGE) wv = *reinterpret_cast<const Vec<float, U> *>(wts + blk + t * U);
+        const unsigned sub = bmask & low_bits<U>();
+        bmask >>= U;
+        if (sub == 0) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) add_edge(v[u], wv.v[u]);
+        } else {
+          // a dst row starts inside these U edges (register buffers: the loop over u must stay unrolled)
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if ((sub >> u) & 1u) {
+              const int k = pos + t * U + u;            // chunk-relative position of this edge
+              const int kb = k - batch_pos;             // position inside the batch
+              const uint32_t row = __shfl_sync(gmask, d_cur, kb > 0 ? kb - 1 : 0, LPR);
+              cnt = k - run_start;
+              close_run((int64_t)(kb > 0 ? row : batch_left));
+              run_start = k;
+            }
+            add_edge(v[u], wv.v[u]);
+          }
+        }
+      };
+
+#pragma unroll 1
+      for (int bi = 0; bi < nfull; ++bi) {
+        const bool has_nn = bi + 2 < nfull;
+        if (has_nn) ld_ops(bi + 2, l_d, l_s, l_w);     // parked at the end of this batch, used from the next one on
+        uint32_t left = __shfl_up_sync(gmask, d_cur, 1, LPR);
+        if (gl == 0) left = ld32;
+        bmask = (__ballot_sync(gmask, d_cur != left) >> gshift) & low_bits<LPR>();
+        batch_left = ld32;
+        ld32 = __shfl_sync(gmask, d_cur, LPR - 1, LPR);
+        batch_pos = pos;
+#pragma unroll 1
+        for (int s0 = 0; s0 < SB; s0 += 2) {
+          const int blk = slot + s0 * U;
+          step(0, blk, va, vb);
+          step(1, blk, vb, va);
+          pos += 2 * U;
+        }
+        // this batch's operand buffer is free: park batch bi+2 there
+        __syncwarp(gmask);
+        if (has_nn) {
+          ids[slot + gl] = l_s;
+          wts[slot + gl] = l_w;
+        }
+        __syncwarp(gmask);
+        slot ^= LPR;
+        d_cur = d_nxt;
+        d_nxt = l_d;
+      }
+      cnt = pos - run_start;
+      // remainder of the edge list's last chunk: one edge at a time, uniform operand loads
+      for (int k = pos; k < n_edges; ++k) {
+        const int64_t e = e_begin + k;
+        const uint32_t d = (uint32_t)dst_index[e];
+        const int64_t sid = src_index ? src_index[e] : e;
+        float we = 1.f;
+        if (WM == WM_EDGE) we = to_acc<T>(weight[e]);
+        VecT v[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + sid * row_bytes);
+        if (d != ld32) close_run((int64_t)ld32);
+        add_edge(v, we);
+        ++cnt;
+        ld32 = d;
+      }
+      last_dst = (int64_t)ld32;
+    } else if constexpr (LEAN) {
       // ---- lean ring (see ShapeOf) ---------------------------------------------------------------------
       constexpr int SB = SH::SB;                   // sub-batches per batch; NS | SB
       constexpr int RING_WORDS = 2 * LPR;          // operand buffers: two batches, circular

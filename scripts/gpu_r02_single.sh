@@ -28,6 +28,12 @@ echo "== zero only the empty rows (GEOT_B200_ZERO_EMPTY) on the workload with ga
 for z in 0 1; do
   GEOT_B200_ZERO_EMPTY=$z timeout 300 python scripts/tune.py arxiv_mh_spmm 0 2>&1 | grep -E "lib=|rror" | sed "s/^/zero_empty=$z /" | tee -a $OUT/zero_empty.txt
 done
+echo "== lean register path (GEOT_B200_RING=96) against the lean ring (35) per workload"
+for wl in reddit_gws products_gs64 products_gs256 proteins_gws256 reddit_index_scatter; do
+  for ring in 35 96; do
+    GEOT_B200_RING=$ring timeout 300 python scripts/tune.py $wl 0 2>&1 | grep -E "lib=|rror" | sed "s/^/ring=$ring /" | tee -a $OUT/ring96_ab.txt
+  done
+done
 echo "== chunk sweep on the two small (latency-bound) workloads"
 for wl in arxiv_mh_spmm config1_index_scatter; do
   timeout 300 python scripts/tune.py $wl 0,16,32,64,128,256 2>&1 | grep -E "lib=|rror" | tee -a $OUT/chunk_sweep_small.txt

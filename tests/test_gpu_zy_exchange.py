@@ -166,3 +166,29 @@ def test_zero_only_the_empty_rows(monkeypatch, dtype, F):
         assert torch.equal(outs[0], outs[1])
         deg = torch.bincount(di.cpu(), minlength=S)
         assert bool((outs[1].cpu()[deg == 0] == 0).all())
+
+
+def test_lean_register_path_bit_identical_and_vs_oracle(monkeypatch):
+    """GEOT_B200_RING=96, the lean register path (experiment, fp32 rows of 256 B - 1 KB; other shapes fall back to
+    the lean ring): walks a chunk in the same order as every other variant, so sums must be bit-identical to the
+    register path (ring 0), and it is checked against the oracle.  Same graphs as the ring-variant test."""
+    import oracle
+    from test_gpu_parity import assert_close, make_graph, run_abi
+    graphs = [(40000 + 37, 60, 0.2, 0.0, 64), (30000 + 5, 9000, 0.0, 0.0, 32), (65536, 500, 0.6, 0.4, 128), (4099, 40, 0.0, 0.0, 256),
+              (200000 + 3, 700, 0.3, 0.2, 0)]
+    for gi, (E, N, skew, hub, chunk) in enumerate(graphs):
+        monkeypatch.setenv("GEOT_B200_CHUNK", str(chunk))
+        si, di, g = make_graph(E, N, seed=100 * gi + 96, skew=skew, hub=hub, gaps=(gi == 1))
+        w = torch.rand(E, generator=g) + 0.25
+        for F in (32, 64, 100, 128, 256, 512):
+            src = torch.rand(N, F, generator=g)
+            for name, (a_si, a_w, a_src) in {"index_scatter": (None, None, src[si]), "gather_scatter": (si, None, src),
+                                             "gather_weight_scatter": (si, w, src)}.items():
+                for reduce in ("sum", "mean"):
+                    monkeypatch.setenv("GEOT_B200_RING", "0")
+                    base = run_abi(a_src, a_si, di, a_w, reduce)
+                    monkeypatch.setenv("GEOT_B200_RING", "96")
+                    got = run_abi(a_src, a_si, di, a_w, reduce)
+                    what = "%s %s ring=96 F=%d graph=%d" % (name, reduce, F, gi)
+                    assert torch.equal(got, base), what
+                    assert_close(got, oracle.segment_reduce(a_src, a_si, di, a_w, reduce, acc64=True), torch.float32, reduce, what)

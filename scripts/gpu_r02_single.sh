@@ -13,7 +13,7 @@ TAG=${1:-r02}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem --format=csv > $OUT/gpu.txt 2>&1
-echo "== pytest -m gpu"; timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
+echo "== pytest -m gpu (experiments included)"; GEOT_B200_TEST_EXPERIMENTS=1 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
 for m in 0 1 3; do
   echo "== bench, host transport $m"
   GEOT_B200_HOST_COMPACT=$m timeout 600 python bench.py --steps 20 --warmup 5 2>$OUT/bench_compact$m.err | tail -1 | tee $OUT/bench_compact$m.json

@@ -240,3 +240,29 @@ def test_shard_bounds_rule():
     assert edges == [0, 9, 20, 30]
     rows1, edges1 = gdist.shard_bounds_from_rowptr(rowptr, 1)
     assert rows1 == [0, 6] and edges1 == [0, 30]
+
+
+def test_shard_bounds_properties_randomised():
+    """shard_bounds_from_rowptr on random degree sequences (hubs, empty rows, more parts than rows): the bounds cover
+    the rows, are monotone, sit on segment boundaries, and every cut is the boundary NEAREST to g*E/parts -- checked
+    against a brute-force search over all boundaries."""
+    from geot_b200 import dist as gdist
+    g = torch.Generator().manual_seed(11)
+    for trial in range(200):
+        S = int(torch.randint(1, 40, (1,), generator=g))
+        deg = torch.randint(0, 6, (S,), generator=g)
+        if trial % 3 == 0:
+            deg[int(torch.randint(0, S, (1,), generator=g))] += int(torch.randint(20, 200, (1,), generator=g))   # a hub
+        if int(deg.sum()) == 0:
+            deg[0] = 1
+        rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)])
+        E = int(rowptr[-1])
+        for parts in (1, 2, 3, 4, 8):
+            rows, edges = gdist.shard_bounds_from_rowptr(rowptr, parts)
+            assert len(rows) == parts + 1 and rows[0] == 0 and rows[-1] == S and edges[0] == 0 and edges[-1] == E
+            assert all(rows[i] <= rows[i + 1] for i in range(parts)) and all(edges[i] <= edges[i + 1] for i in range(parts))
+            assert edges == [int(rowptr[r]) for r in rows]
+            for gi in range(1, parts):
+                target = (E // parts) * gi + ((E % parts) * gi) // parts
+                best = int((rowptr - target).abs().min())
+                assert abs(edges[gi] - target) == best, (trial, parts, gi, edges, target)

@@ -20,7 +20,7 @@ run() {   # run <file stem> <env assignments...> -- bench args
 }
 date +%s > $OUT/t0
 echo "== NCCL parity tests"
-timeout 400 python -m pytest tests/test_gpu_multi.py tests/test_gpu_zz_multi_needed.py -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_multi.txt
+GEOT_B200_TEST_EXPERIMENTS=1 timeout 400 python -m pytest tests/test_gpu_multi.py tests/test_gpu_zz_multi_needed.py -q -m gpu 2>&1 | tail -15 | tee $OUT/pytest_multi.txt
 run reddit_gws_pipeline X=1 -- --steps 10 --warmup 3
 for ex in pipeline needed push allgather replicated; do
   run products_gs64_$ex GEOT_B200_EXCHANGE=$ex -- --workload products_gs64 --steps 10 --warmup 3

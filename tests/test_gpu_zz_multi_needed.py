@@ -117,6 +117,9 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.skipif(os.environ.get("GEOT_B200_TEST_EXPERIMENTS") != "1",
+                    reason="needed-rows / peer-push exchanges were built after the round's GPU budget was spent and have never "
+                           "run on hardware: enable with GEOT_B200_TEST_EXPERIMENTS=1 (scripts/gpu_r02_multi.sh does)")
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_gpu_needed_rows_nccl():
     world = 2
@@ -128,5 +131,9 @@ def test_two_gpu_needed_rows_nccl():
         p.start()
     for p in procs:
         p.join(timeout=600)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    codes = [p.exitcode for p in procs]
+    for p in procs:                     # a rank stuck in a collective must not outlive the test
+        if p.is_alive():
+            p.kill()
+    assert all(c == 0 for c in codes), codes
     assert sorted(q.get(timeout=5) for _ in range(world)) == [0, 1]

@@ -18,6 +18,10 @@ for m in 0 1 3; do
   echo "== bench, host transport $m"
   GEOT_B200_HOST_COMPACT=$m timeout 600 python bench.py --steps 20 --warmup 5 2>$OUT/bench_compact$m.err | tail -1 | tee $OUT/bench_compact$m.json
 done
+echo "== ncu launch list of the default bench command (current build)"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 3 --warmup 3 > $OUT/bench_under_ncu.log 2>&1
+grep -c geot $OUT/launches.csv
 echo "== bf16 max: U0 = 8 (default library) vs U0 = 4 (variant)"
 for lib in default geot_b200/lib/libgeot_b200_u4.so; do
   [ "$lib" = default ] || export GEOT_B200_LIB=$PWD/$lib

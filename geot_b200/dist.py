@@ -419,6 +419,13 @@ class PipelinedGather:
         return (self.needed.recv_offsets[-1] if self.needed is not None else full), full
 
 
+@dataclass
+class _PeerBuffer:
+    """A symmetric-memory receive buffer as the default (CUDA) path of PeerPushGather holds it."""
+    handle: object                   # torch _SymmetricMemory: barrier(channel)
+    bases: torch.Tensor              # [world] int64 on the device: every peer's mapped base address of the buffer
+
+
 class PeerPushGather(PipelinedGather):
     """``gather_(weight_)scatter`` on a dst-row shard with the needed src rows PUSHED over peer memory (sum / mean).
 
@@ -491,7 +498,9 @@ class PeerPushGather(PipelinedGather):
                     pass
                 buf = symm.empty(shape, dtype=dtype, device=device)
                 hdl = symm.rendezvous(buf, pg)
-                self._bufs[key] = (buf, hdl)
+                # the peers' mapped base addresses as a device array (what geot_b200_push_rows indexes by dest_peer)
+                bases = torch.tensor([int(a) for a in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+                self._bufs[key] = (buf, _PeerBuffer(hdl, bases))
         return self._bufs[key]
 
     def _push(self, x_mine, buf, hdl):
@@ -502,13 +511,13 @@ class PeerPushGather(PipelinedGather):
         if nd.send_rows.numel() == 0:
             return
         from . import abi
-        abi.push_rows(x_mine, nd.send_rows, self.dest_peer, self.dest_row, hdl.buffer_ptrs_dev)
+        abi.push_rows(x_mine, nd.send_rows, self.dest_peer, self.dest_row, hdl.bases.data_ptr())
 
     def _barrier(self, hdl, channel):
         if self._barrier_fn is not None:
             self._barrier_fn(hdl, channel)
         else:
-            hdl.barrier(channel=channel)
+            hdl.handle.barrier(channel=channel)
 
     def aggregate(self, x_local, weight=None, reduce="sum"):
         return self(x_local, weight, reduce)

@@ -176,6 +176,43 @@ def _worker(rank, world, port, q, hub=False):
                     else oracle.gather_scatter(src_index, dst, x, reduce))
             assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), ("push", reduce)
 
+    # the DEFAULT branches of PeerPushGather (torch symmetric memory + abi.push_rows), with those two modules faked:
+    # symm.empty / rendezvous hand out local buffers with a barrier, abi.push_rows delivers over gloo like `pusher`
+    import torch.distributed._symmetric_memory as symm
+    from geot_b200 import abi
+
+    class FakeHandle:
+        live = []
+
+        def __init__(self, buf):
+            self.buf, self.buffer_ptrs = buf, [buf.data_ptr() + 4096 * r for r in range(world)]
+            FakeHandle.live.append(self)
+
+        def barrier(self, channel=0):
+            dist.barrier()
+
+    def fake_push_rows(x_mine, rows, dest_peer, dest_row, bases_ptr, aligned16=True):
+        h = [h for h in FakeHandle.live if list(h.buf.shape[1:]) == list(x_mine.shape[1:]) and h.buf.dtype == x_mine.dtype][-1]
+        pusher(x_mine, rows, dest_peer, dest_row, h.buf, None)
+
+    real = (symm.empty, symm.rendezvous, abi.push_rows)
+    symm.empty = lambda shape, dtype=None, device=None: torch.full(list(shape), float("nan"), dtype=dtype)
+    symm.rendezvous = lambda t, group: FakeHandle(t)
+    abi.push_rows = fake_push_rows
+    try:
+        pd = holder["pp"] = gdist.PeerPushGather(shard, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm])
+        # (a rank with nothing to send skips abi.push_rows on the default path but must still receive in this emulation)
+        if pd.requests.send_rows.numel() == 0:
+            pd._pusher = pusher
+        for reduce in ["sum", "mean"]:
+            got = pd(x_local.clone(), shard.weight, reduce)
+            full = oracle.gather_weight_scatter(src_index, dst, weight, x, reduce)
+            assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), ("push default branches", reduce)
+        buf, pb = pd._buffer([F], x_local.dtype, x_local.device)
+        assert pb.bases.tolist() == pb.handle.buffer_ptrs and pb.bases.dtype == torch.int64
+    finally:
+        symm.empty, symm.rendezvous, abi.push_rows = real
+
     # multi-head rows [N, H, F] with per-head weights [E, H] (mh_spmm) through all three overlapped forms
     Hh = 3
     xh = torch.rand(N, Hh, 4, generator=g)

@@ -7,6 +7,8 @@
 # 4. Reddit gws with the needed-rows and all-gather forms, Reddit index_scatter (no exchange).
 N=${1:-2}
 TAG=${2:-r02_n$N}
+# box time is charged N x: at N >= 4 only the essential legs run unless "full" is given as the third argument
+MODE=${3:-$([ "$N" -ge 4 ] && echo short || echo full)}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 run() {   # run <file stem> <env assignments...> -- bench args
@@ -25,14 +27,16 @@ run reddit_gws_pipeline X=1 -- --steps 10 --warmup 3
 for ex in pipeline needed push allgather replicated; do
   run products_gs64_$ex GEOT_B200_EXCHANGE=$ex -- --workload products_gs64 --steps 10 --warmup 3
 done
-for ex in pipeline needed push replicated; do
-  run products_gs256_$ex GEOT_B200_EXCHANGE=$ex -- --workload products_gs256 --steps 10 --warmup 3
-done
 run reddit_gws_push GEOT_B200_EXCHANGE=push -- --steps 10 --warmup 3
-run reddit_gws_needed GEOT_B200_EXCHANGE=needed -- --steps 10 --warmup 3
-run reddit_gws_allgather GEOT_B200_EXCHANGE=allgather -- --steps 10 --warmup 3
-run reddit_gws_replicated GEOT_B200_EXCHANGE=replicated -- --steps 10 --warmup 3
-run reddit_index_scatter X=1 -- --workload reddit_index_scatter --steps 5 --warmup 3
+if [ "$MODE" = full ]; then
+  for ex in pipeline needed push replicated; do
+    run products_gs256_$ex GEOT_B200_EXCHANGE=$ex -- --workload products_gs256 --steps 10 --warmup 3
+  done
+  run reddit_gws_needed GEOT_B200_EXCHANGE=needed -- --steps 10 --warmup 3
+  run reddit_gws_allgather GEOT_B200_EXCHANGE=allgather -- --steps 10 --warmup 3
+  run reddit_gws_replicated GEOT_B200_EXCHANGE=replicated -- --steps 10 --warmup 3
+  run reddit_index_scatter X=1 -- --workload reddit_index_scatter --steps 5 --warmup 3
+fi
 echo "== 3-layer GCN / GraphSAGE forward on the shards (configs[4])"
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     scripts/bench_model_multi.py > $OUT/model.jsonl 2> $OUT/model.err

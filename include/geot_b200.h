@@ -3,7 +3,7 @@
  *
  * This is the drop-in boundary for GeoT's hot path: every entry point replaces one host entry point
  * of the reference's CUDA layer (declared in /root/reference/csrc/cuda/header_cuda.h:4-38) and is
- * what the reference's torch bindings (csrc/*.cpp) bind after the swap -- see INTEGRATION.md.
+ * what the reference's torch bindings (csrc/<op>.cpp) bind after the swap -- see INTEGRATION.md.
  *
  *   - plain pointers and sizes only: no ATen / torch types cross this boundary;
  *   - every function returns a geot_status_t and never throws;

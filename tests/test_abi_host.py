@@ -138,3 +138,23 @@ def test_host_row_pointers_match_the_oracle(threads):
         sl = di[e0:].contiguous()
         got = abi.host_row_pointers(sl, r0, S - r0, threads)
         assert torch.equal(got, exp[r0:] - e0)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/geot_b200.h compiles as C99 (no C++, no torch types) and a C host links against the library: the
+    example a cgo / JNI maintainer would start from (examples/abi_host_example.c).  The pure-host helper runs here;
+    the device call reports the missing GPU through the status code instead of crashing (no CPU path)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_host_example")
+    libdir = os.path.join(root, "geot_b200", "lib")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(root, "include"),
+           os.path.join(root, "examples", "abi_host_example.c"), "-L" + libdir, "-lgeot_b200", "-Wl,-rpath," + libdir, "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert "rowptr: 0 2 3 3 6" in run.stdout, run.stdout + run.stderr
+    if torch.cuda.is_available():
+        assert "dst[3] = 20 200" in run.stdout and "dst[2] = 0 0" in run.stdout and run.returncode == 0
+    else:
+        assert run.returncode == 0 and "CUDA error" in run.stdout, run.stdout + run.stderr

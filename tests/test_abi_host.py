@@ -158,3 +158,20 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
         assert "dst[3] = 20 200" in run.stdout and "dst[2] = 0 0" in run.stdout and run.returncode == 0
     else:
         assert run.returncode == 0 and "CUDA error" in run.stdout, run.stdout + run.stderr
+
+
+def test_library_has_no_torch_dependency_and_exports_only_the_abi():
+    """The boundary is a plain C-ABI library: it links the CUDA runtime and the C/C++ runtimes, nothing of torch / ATen /
+    Python, and its dynamic symbol table defines only geot_b200_* functions (everything else is hidden)."""
+    import subprocess
+    lib = geot_b200.LIB_PATH
+    needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
+    libs = re.findall(r"Shared library: \[([^\]]+)\]", needed)
+    assert libs, needed
+    assert not [l for l in libs if re.search(r"torch|c10|python|aten|nccl", l, re.I)], libs
+    assert any(l.startswith("libcudart") for l in libs), libs
+    syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    defined = [ln.split()[-1] for ln in syms.splitlines() if len(ln.split()) >= 3 and ln.split()[-2] in ("T", "t")]
+    foreign = [s for s in defined if not s.startswith("geot_b200_") and s not in ("_init", "_fini")]
+    assert foreign == [], foreign[:10]
+    assert sorted(set(defined) - {"_init", "_fini"}) == sorted(abi.SYMBOLS)

@@ -175,3 +175,33 @@ def test_library_has_no_torch_dependency_and_exports_only_the_abi():
     foreign = [s for s in defined if not s.startswith("geot_b200_") and s not in ("_init", "_fini")]
     assert foreign == [], foreign[:10]
     assert sorted(set(defined) - {"_init", "_fini"}) == sorted(abi.SYMBOLS)
+
+
+def test_ctypes_binding_matches_the_header_arity_and_types():
+    """geot_b200/abi.py declares argtypes by hand: every function's arity and the pointer / integer class of every
+    argument must agree with include/geot_b200.h (a wrong argtypes entry corrupts arguments silently)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "geot_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    L = abi.lib()
+    checked = 0
+    for m in re.finditer(r"GEOT_API\s+([\w\s\*]+?)\s*\b(geot_b200_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            assert not params or name in ("geot_b200_profile_enable", "geot_b200_profile_read", "geot_b200_status_string"), name
+            continue
+        assert len(fn.argtypes) == len(params), (name, len(fn.argtypes), params)
+        for at, p in zip(fn.argtypes, params):
+            is_ptr = "*" in p or "cudaStream_t" in p
+            if is_ptr:
+                assert at is ctypes.c_void_p or hasattr(at, "contents") or issubclass(at, ctypes._Pointer), (name, p, at)
+            elif "int64_t" in p:
+                assert at is ctypes.c_int64, (name, p, at)
+            elif "size_t" in p:
+                assert at is ctypes.c_size_t, (name, p, at)
+            else:
+                assert at is ctypes.c_int, (name, p, at)
+        checked += 1
+    assert checked >= 18, checked

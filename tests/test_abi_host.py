@@ -205,3 +205,16 @@ def test_ctypes_binding_matches_the_header_arity_and_types():
                 assert at is ctypes.c_int, (name, p, at)
         checked += 1
     assert checked >= 18, checked
+
+
+def test_reference_side_binding_compiles(tmp_path):
+    """INTEGRATION.md section 2 as a real translation unit (examples/reference_binding_gws.cpp): the body GeoT's
+    csrc/gather_weight_scatter.cpp gets after the swap compiles against the torch headers and include/geot_b200.h."""
+    import subprocess
+    from torch.utils.cpp_extension import include_paths
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = (["g++", "-std=c++17", "-O0", "-fPIC", "-c", os.path.join(root, "examples", "reference_binding_gws.cpp"),
+            "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include", "-o", str(tmp_path / "binding.o")]
+           + ["-I" + p for p in include_paths()])
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]

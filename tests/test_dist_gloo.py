@@ -1,4 +1,4 @@
-"""world_size-2 and -4 `gloo` tests of the multi-GPU host logic (geot_b200/dist.py) on CPU.
+"""world_size-2, -4 and -8 `gloo` tests of the multi-GPU host logic (geot_b200/dist.py) on CPU.
 
 The reduction kernels need a GPU, so here each rank reduces its shard with the CPU oracle (used as the
 checker of the sharding logic): edge-balanced bounds, local index rebasing, ragged all-gather of src
@@ -253,7 +253,7 @@ def _worker(rank, world, port, q, hub=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,hub", [(2, False), (4, False), (4, True)])
+@pytest.mark.parametrize("world,hub", [(2, False), (4, False), (4, True), (8, True)])
 def test_sharding_gloo(world, hub):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

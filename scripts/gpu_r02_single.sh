@@ -22,12 +22,6 @@ echo "== ncu launch list of the default bench command (current build)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 > $OUT/bench_under_ncu.log 2>&1
 grep -c geot $OUT/launches.csv
-echo "== bf16 max: U0 = 8 (default library) vs U0 = 4 (variant)"
-for lib in default geot_b200/lib/libgeot_b200_u4.so; do
-  [ "$lib" = default ] || export GEOT_B200_LIB=$PWD/$lib
-  timeout 300 python scripts/bench_reduce_ops.py 2>&1 | sed "s|^|lib=$lib |" | tee -a $OUT/bf16_u0.txt
-done
-unset GEOT_B200_LIB
 echo "== zero only the empty rows (GEOT_B200_ZERO_EMPTY) on the workload with gaps"
 for z in 0 1; do
   GEOT_B200_ZERO_EMPTY=$z timeout 300 python scripts/tune.py arxiv_mh_spmm 0 2>&1 | grep -E "lib=|rror" | sed "s/^/zero_empty=$z /" | tee -a $OUT/zero_empty.txt

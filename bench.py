@@ -9,19 +9,30 @@ synthetic Reddit-shape graph (232,965 nodes, 114,615,892 (dst,src)-sorted edges,
 
   value      effective GB/s = algorithmic ("logical") bytes per step / time, inputs resident in HBM,
              called through the C ABI (libgeot_b200.so) with a cached format_preprocess plan.
-  e2e        the same metric through the host-buffer C-ABI entry (geot_b200_segment_reduce_host):
-             pinned HOST operands, H2D copies + kernel + D2H of the result inside the timed region.
+  e2e        the same metric with HOST operands through the C ABI's resident host graph
+             (geot_b200_host_graph_reduce: the static index arrays were uploaded once at create; every
+             step copies src + weights host->device from pinned memory and the result device->host,
+             inside the timed region).  The stateless host entry (geot_b200_segment_reduce_host, which
+             also ships the index arrays every call) is timed beside it.
   roofline   the dominant kernel (segment_reduce_kernel) timed with CUDA events recorded by the library
-             around that kernel alone, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+             around that kernel alone, against the measured HBM copy bandwidth (MEASURED_PEAKS.json);
+             three fractions: on logical bytes, on the DRAM bytes ncu counted, on compulsory bytes.
   cpu_baseline  the CPU restatement of the reference (oracle/, OpenMP over all host cores; torch's
              index_select*mul+index_add_ beside it) on a bounded sample of the same workload.
+  parity     the timed configuration's own output checked in the same run: counting property (src = 1
+             => in-degree, exact) and sampled rows (hubs included) against the CPU oracle.
+  secondary  the other BASELINE.json configurations (N = 1: index_scatter on the Reddit shape and on
+             config #1 with the reference's CPU path timed beside it, products gather_scatter, arxiv
+             mh_spmm; N > 1: products gather_scatter F = 64 / 256, exchange-inclusive and pre-replicated).
 
 --impl reference times the reference's CPU side of the path on the host cores (GeoT ships a CPU kernel
 for index_scatter only -- numerically wrong, SURVEY 8a A5 -- and none for gather_weight_scatter, so the
 arm is the oracle port / torch restatement; where oracle/_ref was built its csrc/cpu kernel is timed too
 and labelled).  N > 1: one process per GPU under torchrun; the dst rows are sharded with balanced edge
-counts, each rank reduces its own slice, the src rows travel over NCCL each step inside the timed region
-(GEOT_B200_EXCHANGE = pipeline [default] | needed | push | allgather | replicated; strong scaling).
+counts, each rank reduces its own slice, the src rows travel each step inside the timed region
+(GEOT_B200_EXCHANGE = bucket [default: all-gather on a side stream overlapped with the src-local edge
+bucket, src-remote bucket accumulated afterwards] | push [needed rows stored into the peers' symmetric
+memory by one kernel] | allgather [one all-gather, then one reduction] | replicated; strong scaling).
 """
 import argparse
 import json
@@ -33,6 +44,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm uses every host core (rank 0 alone runs it)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 import torch  # noqa: E402
 
@@ -47,6 +62,15 @@ WORKLOADS = {
     "config1_index_scatter": ("config1", "index_scatter", 64, 1, torch.float32),
 }
 DTYPE_NAME = {torch.float32: "f32", torch.float64: "f64", torch.bfloat16: "bf16", torch.float16: "f16"}
+EXCHANGES = {
+    "bucket": "one ragged NCCL all-gather on a side stream, overlapped with the reduction of the src-local edge bucket; "
+              "the src-remote bucket is accumulated into the same output afterwards (2 reductions, no combine pass)",
+    "push": "ONE kernel stores the rows the peers' edges reference straight into their symmetric-memory buffers over "
+            "NVLink (no NCCL on the data path), overlapped with the src-local edge bucket; src-remote bucket afterwards",
+    "allgather": "one NCCL all-gather, then one reduction",
+    "replicated": "NONE inside the step (src pre-replicated: kernel scaling only, SURVEY 8e)",
+    "none": "no exchange (edge-aligned operands)",
+}
 
 
 def measured_peak_gbs():
@@ -136,6 +160,8 @@ def build_workload(name, device, scale=1.0):
                 bytes_logical=wl.bytes_logical(op, E, S, N, F, H, s), bytes_compulsory=wl.bytes_compulsory(op, E, S, N, F, H, s))
 
 
+# ---- CPU arm -----------------------------------------------------------------------------------------
+
 def cpu_sample(wk, frac_edges=1.0 / 16, max_edges=8_000_000):
     """Bounded CPU-side sample of the workload: a prefix of the sorted edge list (whole segments)."""
     E = wk["E"]
@@ -147,7 +173,7 @@ def cpu_sample(wk, frac_edges=1.0 / 16, max_edges=8_000_000):
     x = wk["x"].cpu() if wk["si"] is not None else wk["x"][:n].cpu()
     import workloads as wl
     nbytes = wl.bytes_logical(wk["op"], n, S, x.shape[0], wk["F"], wk["H"], wk["esize"])
-    return dict(n=n, S=S, di=di, si=si, w=w, x=x, bytes=nbytes)
+    return dict(n=n, S=S, di=di, si=si, w=w, x=x, bytes=nbytes, fraction=n / E)
 
 
 def time_cpu(fn, warmup, steps):
@@ -160,8 +186,12 @@ def time_cpu(fn, warmup, steps):
 
 
 def cpu_arm(wk, warmup, steps):
-    """Times the CPU restatements on a bounded sample.  Returns the cpu_baseline object + per-step seconds."""
+    """Times the CPU restatements on a bounded sample with every host core.  Returns the cpu_baseline object, the
+    per-step seconds of the fastest one and the sample fraction."""
     import oracle
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)                    # (torchrun workers start with OMP_NUM_THREADS=1)
+    cores = oracle.set_threads(ncpu)
     sm = cpu_sample(wk)
     H = wk["H"]
     res = {}
@@ -182,17 +212,19 @@ def cpu_arm(wk, warmup, steps):
     res["torch_restatement"] = time_cpu(torch_fn, warmup, steps)
     kind = "port"
     if wk["op"] == "index_scatter" and wk["dtype"] == torch.float32 and oracle.load_ref_extension():
+        # the reference's own CPU kernel (csrc/cpu/index_scatter_cpu.cpp:136-155), unmodified, compiled by oracle/Makefile.ref
         ref = lambda: torch.ops.geot_ref.index_scatter(0, sm["di"], sm["x"], "sum", True)
         res["reference_csrc_cpu_NUMERICALLY_WRONG_A5"] = time_cpu(ref, warmup, steps)
-    best = min(res, key=lambda k: res[k][0])
-    cores = max(torch.get_num_threads(), 1)
+    best = min((k for k in res if "WRONG" not in k), key=lambda k: res[k][0])
     gbs = {k: sm["bytes"] / v[0] / 1e9 for k, v in res.items()}
-    sample = ("first %d of %d edges (%d dst rows) of the workload, sum; GB/s on the sample's logical bytes; avg of %d runs: "
-              % (sm["n"], wk["E"], sm["S"], steps) + ", ".join("%s %.2f GB/s" % (k, v) for k, v in gbs.items())
-              + "; os.cpu_count=%s torch_threads=%d" % (os.cpu_count(), torch.get_num_threads()))
+    sample = ("first %d of %d edges (%d dst rows; fraction %.4f) of the workload, sum; GB/s on the sample's logical bytes; avg of "
+              "%d runs: " % (sm["n"], wk["E"], sm["S"], sm["fraction"], steps)
+              + ", ".join("%s %.2f GB/s" % (k, v) for k, v in gbs.items())
+              + "; os.cpu_count=%s omp_threads=%d torch_threads=%d" % (os.cpu_count(), cores, torch.get_num_threads()))
     obj = {"value": round(gbs[best], 3), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample,
-           "edges_per_s": sm["n"] / res[best][0], "which": best}
-    return obj, res[best][0]
+           "sample_fraction": round(sm["fraction"], 6), "edges_per_s": sm["n"] / res[best][0], "which": best,
+           "all_gbs": {k: round(v, 3) for k, v in gbs.items()}}
+    return obj, res[best][0], sm["fraction"]
 
 
 def run_reference(args):
@@ -203,12 +235,17 @@ def run_reference(args):
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     scale = 1.0 if dev == "cuda" else 1.0 / 16
     wk = build_workload(args.workload, dev, scale)
-    obj, sec = cpu_arm(wk, max(1, min(args.warmup, 2)), max(1, min(args.steps, 5)))
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    obj, sec, frac = cpu_arm(wk, warmup, steps)
+    assert obj["cores"] > 1 or (os.cpu_count() or 1) == 1, "the CPU arm must use every host core"
+    cfg = config_of(wk, args.gpus)
+    cfg["sample_fraction"] = round(frac, 6)
+    cfg["sample"] = "each step = the first %.4f of the workload's sorted edge list (whole segments)" % frac
     line = {
         "impl": "reference", "metric": metric_name(wk), "value": obj["value"], "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": sec * 1e3,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE_NAME[wk["dtype"]],
-        "data": "synthetic", "config": config_of(wk, args.gpus),
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": obj,
         "e2e": {"value": obj["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "edges_per_s": obj["edges_per_s"], "gpu_launches": 0,
@@ -220,7 +257,7 @@ def metric_name(wk):
     return "%s effective GB/s (logical bytes / time)" % wk["op"]
 
 
-def config_of(wk, n_gpus, exchange="allgather"):
+def config_of(wk, n_gpus, exchange="none"):
     g = wk["graph"]
     return {"workload": "%s: %s on synthetic %s-shape graph, %d nodes, %d (dst,src)-sorted edges, F=%d%s, %s" % (
                 wk["name"], wk["op"], g.name, wk["N"], wk["E"], wk["F"], (" x H=%d" % wk["H"]) if wk["H"] > 1 else "",
@@ -231,14 +268,350 @@ def config_of(wk, n_gpus, exchange="allgather"):
             "l2": "per-step input streams (%.2f GB) exceed the 126 MB L2; no explicit flush" % (
                 (wk["bytes_compulsory"]) / 1e9),
             "parallelism": "1 GPU" if n_gpus == 1 else "dst rows sharded over %d GPUs (edge-balanced); src rows per step: %s" % (
-                n_gpus, {"pipeline": "staggered NCCL send/recv steps overlapped with per-owner edge buckets",
-                         "needed": "staggered NCCL send/recv of ONLY the rows each bucket references (packed per peer), "
-                                   "overlapped with per-owner edge buckets",
-                         "push": "ONE kernel stores the referenced rows straight into the requesters' symmetric-memory buffers "
-                                 "over NVLink (no NCCL on the data path), overlapped with the local-src edge bucket",
-                         "allgather": "one NCCL all-gather, then one reduction",
-                         "replicated": "NONE inside the step (src pre-replicated: kernel scaling only, SURVEY 8e)",
-                         "none": "no exchange (edge-aligned operands)"}[exchange])}
+                n_gpus, EXCHANGES[exchange])}
+
+
+# ---- the GPU arm -------------------------------------------------------------------------------------
+
+class Runner:
+    """One workload set up for timing on this rank: the shard (N > 1), the exchange form, preallocated output and
+    scratch, and `step()` = one pass of the hot path through the C ABI."""
+
+    def __init__(self, wk, world, rank, dev, exchange):
+        from geot_b200 import abi
+        from geot_b200 import dist as gdist
+        self.wk, self.world, self.rank, self.dev = wk, world, rank, dev
+        self.abi, self.gdist = abi, gdist
+        op, H = wk["op"], wk["H"]
+        self.gather = op != "index_scatter"
+        w = wk["w"]
+        self.layout = abi.W_NONE if w is None else (abi.W_EDGE if w.dim() == 1 else abi.W_EDGE_HEAD)
+        self.exchange = exchange if (world > 1 and self.gather) else "none"
+        self.shard, self.bg, self.imbalance, self.exchanged = None, None, 1.0, None
+        tail = list(wk["x"].shape[1:])
+        if world > 1:
+            sh = self.shard = gdist.shard_graph(wk["si"], wk["di"], w, rank, world)
+            self.imbalance = sh.imbalance
+            rb = sh.row_bounds
+            e0, e1 = sh.edge_bounds[rank], sh.edge_bounds[rank + 1]
+            self.di, self.si, self.w, self.S = sh.dst_index, sh.src_index, sh.weight, sh.num_local_rows
+            self.row0 = rb[rank]
+            self.x_edges = wk["x"][e0:e1].contiguous() if not self.gather else None
+            self.x_local = wk["x"][rb[rank]:rb[rank + 1]].contiguous() if self.gather else None
+            self.x_full = None
+            if self.exchange in ("allgather", "replicated"):
+                self.x_full = torch.empty([wk["N"]] + tail, dtype=wk["dtype"], device=dev)
+            if self.exchange == "replicated":
+                gdist.all_gather_rows(self.x_local, rb, out=self.x_full)
+            if self.exchange in ("bucket", "push"):
+                self.bg = gdist.BucketedGather(sh, transport="push" if self.exchange == "push" else "allgather")
+                self.exchanged = self.bg.exchanged_rows()
+        else:
+            self.di, self.si, self.w, self.S, self.row0 = wk["di"], wk["si"], w, wk["S"], 0
+        self.E = self.di.numel()
+        self.W = wk["F"] * H
+        self.out = torch.empty([self.S] + tail, dtype=wk["dtype"], device=dev)
+        self.plan = self.ws = None
+        if self.bg is None and self.E > 0:
+            self.plan = abi.DevicePlan(self.di, self.S)
+            self.ws = abi.Workspace(self.E, self.W, wk["dtype"], dev)
+        self.calls_per_step = 2 if self.bg is not None else 1
+        per_head_perm = 1 if (self.bg is not None and w is not None and w.dim() == 2) else 0
+        # this library's kernels per step: main + fixup per reduction (+ the push kernel, + the per-head weight permutation)
+        self.launches_per_step = 2 * self.calls_per_step + (1 if self.exchange == "push" else 0) + per_head_perm
+
+    def reduce(self, x, w, out, reduce="sum"):
+        """The op on this rank's operands: x = full src (N = 1) / this rank's src rows (N > 1 gather) / edge rows."""
+        wk, abi = self.wk, self.abi
+        if self.E == 0:
+            return out.zero_()
+        if self.bg is not None:
+            return self.bg(x, w, reduce, out=out)
+        if self.exchange == "allgather":
+            x = self.gdist.all_gather_rows(x, self.shard.row_bounds, out=self.x_full)
+        elif self.exchange == "replicated":
+            # the timed step reads the pre-replicated matrix; any other operand (the parity check's) is gathered afresh
+            x = self.x_full if x is self.x_local else self.gdist.all_gather_rows(x, self.shard.row_bounds)
+        return abi.segment_reduce(x, self.si, self.di, w, reduce, S=self.S, H=wk["H"], weight_layout=self.layout if w is not None else abi.W_NONE,
+                                  plan=self.plan, out=out, workspace=self.ws)
+
+    def src_operand(self):
+        if self.world == 1:
+            return self.wk["x"]
+        return self.x_local if self.gather else self.x_edges
+
+    def step(self):
+        self.reduce(self.src_operand(), self.w, self.out)
+
+
+def barrier(world):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def time_runner(r, steps, warmup, sampler=None):
+    """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream, max
+    over ranks.  Returns (ms per step, main-kernel ms per step)."""
+    import torch.distributed as dist
+    abi = r.abi
+    for _ in range(max(warmup, 3)):
+        r.step()
+    abi.profile_enable(steps * r.calls_per_step)
+    if sampler is not None:
+        sampler.start()
+    barrier(r.world)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(steps):
+        r.step()
+    ev[1].record()
+    barrier(r.world)
+    total_ms = ev[0].elapsed_time(ev[1])
+    kernel_ms = abi.profile_read(steps * r.calls_per_step)
+    abi.profile_enable(0)
+    kmean = (sum(kernel_ms) / steps) if kernel_ms else 0.0
+    if r.world > 1:
+        t = torch.tensor([total_ms, kmean], device=r.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kmean = t.tolist()
+    return total_ms / steps, kmean
+
+
+def parity_check(r, rows_k=40):
+    """The timed configuration checked in the same run (the oracle is the checker only): (1) counting -- src = 1,
+    weight = 1 => every output element equals its row's in-degree (exact in fp32; bf16 within 1e-2); (2) the timed
+    step's own output on sampled rows (the 3 largest hubs, first, last, random ones) against the CPU oracle recomputed
+    from the rows' edge slices (fp64 accumulation; 1e-5 relative for fp32, 1e-2 for bf16).  All-reduced over ranks."""
+    import oracle
+    import torch.distributed as dist
+    wk = r.wk
+    dtype = wk["dtype"]
+    tol = 1e-5 if dtype in (torch.float32, torch.float64) else 1e-2
+    res = {"counting_ok": True, "rows_ok": True, "rows_checked": 0, "max_rel_err": 0.0}
+    if r.E > 0 and r.S > 0:
+        deg = torch.bincount(r.di, minlength=r.S)
+        src = r.src_operand()
+        ones = torch.ones_like(src)
+        w1 = torch.ones_like(r.w) if r.w is not None else None
+        out = torch.full_like(r.out, 3.0)
+        r.reduce(ones, w1, out)
+        exp = deg.to(torch.float32).view([-1] + [1] * (out.dim() - 1)).expand_as(out)
+        if dtype == torch.float32:
+            res["counting_ok"] = bool(torch.equal(out, exp))
+        else:
+            res["counting_ok"] = bool(((out.float() - exp).abs() <= 1e-2 * exp).all())
+        del ones, w1, out, exp
+        # sampled rows of the timed step's output
+        r.step()
+        torch.cuda.synchronize()
+        rowptr = torch.cat([deg.new_zeros(1), deg.cumsum(0)]).cpu()
+        g = torch.Generator().manual_seed(1234 + r.rank)
+        rows = torch.unique(torch.cat([torch.randint(0, r.S, (rows_k,), generator=g), torch.topk(deg.cpu(), min(3, r.S)).indices,
+                                       torch.tensor([0, r.S - 1])]))
+        x_all = wk["x"]                                   # full src (gather ops) / all edge rows (index_scatter)
+        e_base = r.shard.edge_bounds[r.rank] if r.shard is not None else 0
+        worst = 0.0
+        for row in rows.tolist():
+            b, e = int(rowptr[row]), int(rowptr[row + 1])
+            got = r.out[row].cpu()
+            if b == e:
+                ok = float(got.abs().sum()) == 0.0
+            else:
+                w = r.w[b:e].cpu() if r.w is not None else None
+                if r.gather:
+                    uniq, inv = torch.unique(r.si[b:e], return_inverse=True)
+                    xs, si = x_all[uniq].cpu(), inv.cpu()
+                else:
+                    xs, si = x_all[e_base + b:e_base + e].cpu(), None
+                expv = oracle.segment_reduce(xs, si, torch.zeros(e - b, dtype=torch.int64), w, "sum", S=1, H=wk["H"],
+                                             acc64=(dtype == torch.float32))[0]
+                err = float(((got.double() - expv.double()).abs() / expv.double().abs().clamp_min(1e-30)).max())
+                worst = max(worst, err)
+                ok = err <= tol
+            res["rows_ok"] = res["rows_ok"] and ok
+            res["rows_checked"] += 1
+        res["max_rel_err"] = worst
+    if r.world > 1:
+        t = torch.tensor([0.0 if res["counting_ok"] else 1.0, 0.0 if res["rows_ok"] else 1.0, res["max_rel_err"]],
+                         device=r.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n = torch.tensor([float(res["rows_checked"])], device=r.dev, dtype=torch.float64)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        res = {"counting_ok": t[0].item() == 0, "rows_ok": t[1].item() == 0, "rows_checked": int(n.item()), "max_rel_err": t[2].item()}
+    res["ok"] = bool(res["counting_ok"] and res["rows_ok"])
+    res["tolerance"] = tol
+    res["max_rel_err"] = float("%.3g" % res["max_rel_err"])
+    res["what"] = ("counting (src=1, weight=1 => in-degree) + the timed output's sampled rows (3 hubs, first, last, random) "
+                   "vs the CPU oracle, every rank, all-reduced")
+    return res
+
+
+def fractions(wk, r, kmean, peak, traffic=None):
+    """The main kernel's three roofline readings (per launch on this rank; N > 1: the slowest rank's time)."""
+    import workloads as wl
+    k_log = wl.bytes_logical(wk["op"], r.E, r.S, wk["N"], wk["F"], wk["H"], wk["esize"])
+    k_comp = wl.bytes_compulsory(wk["op"], r.E, r.S, wk["N"], wk["F"], wk["H"], wk["esize"])
+    if kmean <= 0:
+        return k_log, k_comp, 0.0, {}
+    achieved = k_log / (kmean * 1e-3) / 1e9
+    f = {"frac_logical": round(achieved / peak, 4), "frac_compulsory": round(k_comp / (kmean * 1e-3) / 1e9 / peak, 4),
+         "frac_dram": round(traffic / (kmean * 1e-3) / 1e9 / peak, 4) if traffic else None}
+    return k_log, k_comp, achieved, f
+
+
+def ncu_traffic(name):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tp)).get(name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def summarize(wk, r, ms, kmean, peak, parity, world):
+    """Compact record of one timed workload (the `secondary` entries)."""
+    traffic = ncu_traffic(wk["name"]) if world == 1 else None
+    _, k_comp, achieved, f = fractions(wk, r, kmean, peak, traffic)
+    d = {"metric": metric_name(wk), "workload": config_of(wk, world, r.exchange)["workload"],
+         "value": round(wk["bytes_logical"] / (ms * 1e-3) / 1e9, 2), "unit": "GB/s", "ms_per_step": round(ms, 4),
+         "edges_per_s": wk["E"] / (ms * 1e-3), "kernel_ms": round(kmean, 4), "kernel_achieved_gbs": round(achieved, 1),
+         "frac_of_measured_hbm": round(wk["bytes_logical"] / (ms * 1e-3) / 1e9 / peak, 4),
+         "bytes_logical_per_step": wk["bytes_logical"], "bytes_compulsory_per_step": wk["bytes_compulsory"],
+         "traffic": traffic, "exchange": r.exchange, "parity": parity}
+    d.update(f)
+    return d
+
+
+def run_secondary(name, world, rank, dev, exchanges, steps, warmup, peak, with_cpu=False):
+    """Builds workload `name` once and times it with every exchange form in `exchanges`; {form: record}."""
+    wk = build_workload(name, dev)
+    res = {}
+    for exchange in exchanges:
+        r = Runner(wk, world, rank, dev, exchange)
+        ms, kmean = time_runner(r, steps, warmup)
+        par = parity_check(r)
+        d = summarize(wk, r, ms, kmean, peak, par, world)
+        if r.exchanged is not None:
+            d["src_rows_received_per_step_rank0"], d["src_rows_full_exchange_rank0"] = r.exchanged
+        d["shard_imbalance"] = round(r.imbalance, 4)
+        if with_cpu and rank == 0:
+            d["cpu_baseline"], _, _ = cpu_arm(wk, 1, 3)
+        res[exchange] = d
+        del r
+        torch.cuda.empty_cache()
+    del wk
+    torch.cuda.empty_cache()
+    return res
+
+
+def e2e_multi(r, wk, world, rank, dev, n_e2e):
+    """e2e at N > 1: every rank's operands start in pinned HOST memory; per step the rank copies ITS OWN src rows (1/N
+    of the matrix) and its edge weights host->device, the src rows are exchanged GPU-to-GPU over NVLink exactly as in
+    the device-resident step, and the rank's dst rows go device->host.  The shard's index arrays are resident (a GNN's
+    graph is static).  Time = max over ranks between two barriers; bytes = sum over ranks."""
+    import torch.distributed as dist
+    ok, moved, e2e_step = 1, [0, 0], None
+    big = (not r.gather) and (r.E * r.W * wk["esize"]) > 8e9          # edge-aligned src too large to pin
+    try:
+        if r.E > 0 and not big:
+            src_dev = r.src_operand()
+            h_x = src_dev.cpu().pin_memory()
+            h_w = r.w.cpu().pin_memory() if r.w is not None else None
+            h_out = torch.empty(r.out.shape, dtype=r.out.dtype).pin_memory()
+            d_x, d_w = torch.empty_like(src_dev), (torch.empty_like(r.w) if r.w is not None else None)
+            moved = [h_x.numel() * h_x.element_size() + (h_w.numel() * h_w.element_size() if h_w is not None else 0),
+                     h_out.numel() * h_out.element_size()]
+
+            def e2e_step():
+                d_x.copy_(h_x, non_blocking=True)
+                if d_w is not None:
+                    d_w.copy_(h_w, non_blocking=True)
+                r.reduce(d_x, d_w, r.out)
+                h_out.copy_(r.out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        elif big:
+            ok = 0
+    except Exception as ex:      # local failure only: the ranks agree on `ok` before any collective of this leg
+        ok = 0
+        print("rank %d: e2e leg failed: %r" % (rank, ex), file=sys.stderr)
+    flag = torch.tensor([float(1 - ok)], device=dev, dtype=torch.float64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if flag.item() != 0:
+        return None
+
+    def one():
+        if e2e_step is not None:
+            e2e_step()
+        elif r.bg is not None or r.exchange == "allgather":     # an empty shard still takes part in the exchange
+            r.reduce(r.src_operand(), r.w, r.out)
+    one()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        one()
+    barrier(world)
+    el = (time.perf_counter() - t0) / n_e2e
+    t = torch.tensor([el], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    b = torch.tensor([float(moved[0]), float(moved[1])], device=dev, dtype=torch.float64)
+    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    e2e_s = t[0].item()
+    return {"value": round(wk["bytes_logical"] / e2e_s / 1e9, 2), "unit": "GB/s",
+            "h2d_bytes_per_step": int(b[0].item()), "d2h_bytes_per_step": int(b[1].item()),
+            "ms_per_step": round(e2e_s * 1e3, 3), "steps": n_e2e, "edges_per_s": wk["E"] / e2e_s,
+            "api": "every rank: pinned host src rows of its own shard + edge weights -> device, geot_b200.dist exchange + "
+                   "C-ABI reduction as in the device-resident step, dst rows -> pinned host; index arrays resident; timed "
+                   "between two barriers, max over ranks; bytes summed over ranks"}
+
+
+def e2e_single(r, wk, n_e2e):
+    """e2e at N == 1: host buffers through the C ABI's resident host graph; the stateless host entry beside it."""
+    abi = r.abi
+    E, S, N, H = wk["E"], wk["S"], wk["N"], wk["H"]
+    hx = wk["x"].cpu().pin_memory()
+    hdi = r.di.cpu().pin_memory()
+    hsi = r.si.cpu().pin_memory() if r.si is not None else None
+    hw = r.w.cpu().pin_memory() if r.w is not None else None
+    hout = torch.empty(r.out.shape, dtype=r.out.dtype).pin_memory()
+    r.step()
+    torch.cuda.synchronize()
+    dev_out = r.out.cpu()
+    layout = r.layout
+    t0 = time.perf_counter()
+    hg = abi.HostGraph(hsi, hdi, S, N if hsi is not None else 0)
+    create_s = time.perf_counter() - t0
+    call = lambda: hg.reduce(hx, hw, "sum", H=H, weight_layout=layout, out=hout)
+    call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        call()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    h2d, d2h, resident = hg.last_transfer()
+    tol = 1e-5 if wk["dtype"] == torch.float32 else 1e-2
+    match = bool(((hout.double() - dev_out.double()).abs() <= 4 * tol * dev_out.double().abs().clamp_min(1e-30)).all())
+    hg.close()
+    st_call = lambda: abi.segment_reduce_host(hx, hsi, hdi, hw, "sum", S=S, H=H, weight_layout=layout, out=hout)
+    st_call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        st_call()
+    torch.cuda.synchronize()
+    st_s = (time.perf_counter() - t0) / 3
+    st_h2d, st_d2h = abi.host_last_transfer()
+    abi.lib().geot_b200_host_arena_release()
+    return {"value": round(wk["bytes_logical"] / e2e_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3), "steps": n_e2e, "edges_per_s": E / e2e_s,
+            "matches_device_result": match,
+            "resident": {"index_bytes_uploaded_once": resident, "create_ms": round(create_s * 1e3, 1)},
+            "api": "geot_b200_host_graph_reduce (C ABI; index arrays uploaded once by geot_b200_host_graph_create, outside the "
+                   "timed region; per step pinned host src + weights H2D, kernels, dst D2H; host wall clock)",
+            "stateless": {"api": "geot_b200_segment_reduce_host (every operand incl. the index arrays from the host each call)",
+                          "ms_per_step": round(st_s * 1e3, 3), "value": round(wk["bytes_logical"] / st_s / 1e9, 2),
+                          "h2d_bytes_per_step": st_h2d, "d2h_bytes_per_step": st_d2h}}
 
 
 def run_own(args):
@@ -251,269 +624,89 @@ def run_own(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    import geot_b200
-    from geot_b200 import abi
-    from geot_b200 import dist as gdist
+    import geot_b200  # noqa: F401
 
+    peak, peak_src = measured_peak_gbs()
+    exchange = os.environ.get("GEOT_B200_EXCHANGE", "bucket")
+    if exchange not in ("bucket", "push", "allgather", "replicated"):
+        raise SystemExit("GEOT_B200_EXCHANGE must be bucket, push, allgather or replicated")
     wk = build_workload(args.workload, dev)
-    E, S, N, F, H = wk["E"], wk["S"], wk["N"], wk["F"], wk["H"]
-    W = F * H
-    x, w, si, di = wk["x"], wk["w"], wk["si"], wk["di"]
-    layout = abi.W_NONE if w is None else (abi.W_EDGE if w.dim() == 1 else abi.W_EDGE_HEAD)
-
-    # ---- shard (N > 1) ------------------------------------------------------------------------------
-    imbalance = 1.0
-    if world > 1:
-        shard = gdist.shard_graph(si, di, w, rank, world)
-        imbalance = shard.imbalance
-        rb = shard.row_bounds
-        e0, e1 = shard.edge_bounds[rank], shard.edge_bounds[rank + 1]
-        l_di, l_si, l_w = shard.dst_index, shard.src_index, shard.weight
-        if wk["op"] == "index_scatter":
-            l_x_edges = x[e0:e1].contiguous()
-        x_local = x[rb[rank]:rb[rank + 1]].contiguous() if wk["op"] != "index_scatter" else None
-        l_S = shard.num_local_rows
-        h_src_full = x.cpu() if wk["op"] != "index_scatter" else None      # the host-resident src matrix of the e2e leg
-        del x, w, si, di
-        torch.cuda.empty_cache()
-    else:
-        l_di, l_si, l_w, l_S = di, si, w, S
-    l_E = l_di.numel()
-    plan = abi.DevicePlan(l_di, l_S)
-    ws = abi.Workspace(l_E, W, wk["dtype"], dev)
-    out = torch.empty([l_S] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device=dev)
-
-    x_full = torch.empty([N] + list(wk["x"].shape[1:]), dtype=wk["dtype"], device=dev) if (world > 1 and wk["op"] != "index_scatter") else None
-    # N > 1, gather ops: how the src row shards travel.  "pipeline" (default): staggered NCCL send/recv steps overlapped
-    # with the reduction of per-owner edge buckets (geot_b200.dist.PipelinedGather); "allgather": one NCCL all-gather,
-    # then one reduction.  Both are inside the timed region.
-    exchange = os.environ.get("GEOT_B200_EXCHANGE", "pipeline") if (world > 1 and wk["op"] != "index_scatter") else "none"
-    if exchange not in ("pipeline", "needed", "push", "allgather", "replicated", "none"):
-        raise SystemExit("GEOT_B200_EXCHANGE must be pipeline, needed, push, allgather or replicated")
-    calls_per_step = 1
-    pg = None
-    if exchange == "replicated":
-        # "src pre-replicated" (SURVEY 8e): every rank already holds all src rows, no exchange inside the step.  This is
-        # the kernel-scaling number reported BESIDE the default (exchange inside the timed region), never instead of it.
-        gdist.all_gather_rows(x_local, rb, out=x_full)
-    exchanged = None
-    if exchange in ("pipeline", "needed", "push"):
-        pg = (gdist.PeerPushGather(shard) if exchange == "push"
-              else gdist.PipelinedGather(shard, needed_only=(exchange == "needed")))
-        exchanged = pg.exchanged_rows()
-        pg.local_rows(x_full).copy_(x_local)
-        calls_per_step = 2 if exchange == "push" else world
-        del ws
-        ws = None
-
-    # opt-in experiment (N = 1, gather ops, one weight per edge at most): temporal blocking of the src matrix for L2
-    blocked, w_blocked = None, None
-    n_blocks = int(os.environ.get("GEOT_B200_SRC_BLOCKS", "0"))
-    if n_blocks > 1 and world == 1 and wk["op"] != "index_scatter" and H == 1:
-        blocked = gdist.SrcBlockedGather(l_si, l_di, l_S, N, n_blocks)
-        w_blocked = blocked.permute_weight(l_w) if l_w is not None else None      # static weights: permuted once
-        calls_per_step = n_blocks
-
-    def step():
-        if blocked is not None:
-            blocked(wk["x"], w_blocked, "sum", out=out, permuted=True)
-            return
-        if pg is not None:
-            pg(x_full, l_w, "sum", out=out)
-            return
-        if exchange == "replicated":
-            xf = x_full
-        elif world > 1 and wk["op"] != "index_scatter":
-            xf = gdist.all_gather_rows(x_local, rb, out=x_full)
-        elif world > 1:
-            xf = l_x_edges
-        else:
-            xf = wk["x"]
-        abi.segment_reduce(xf, l_si, l_di, l_w, "sum", S=l_S, H=H, weight_layout=layout, plan=plan, out=out, workspace=ws)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # opt-in experiment (off by default): pin the src feature matrix in the persisting L2 set-aside
-    l2_note = None
-    if os.environ.get("GEOT_B200_L2_PERSIST", "0") == "1" and wk["op"] != "index_scatter":
-        try:
-            win, carve = abi.l2_persist(x_full if x_full is not None else wk["x"])
-            l2_note = "src pinned in persisting L2: window %d B, carve-out %d B" % (win, carve)
-        except abi.AbiError as e:
-            l2_note = "l2_persist unavailable: %s" % e
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    abi.profile_enable(args.steps * calls_per_step)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(args.steps):
-        step()
-    ev[1].record()
-    barrier()
-    total_ms = ev[0].elapsed_time(ev[1])
-    kernel_ms = abi.profile_read(args.steps * calls_per_step)     # pipelined exchange: one main-kernel launch per bucket
-    abi.profile_enable(0)
+    r = Runner(wk, world, rank, dev, exchange)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_per_step, kmean = time_runner(r, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([total_ms, sum(kernel_ms) / args.steps], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kmean = t.tolist()
-    else:
-        kmean = sum(kernel_ms) / args.steps
-    ms_per_step = total_ms / args.steps
     value = wk["bytes_logical"] / (ms_per_step * 1e-3) / 1e9
+    parity = parity_check(r)
 
-    # ---- e2e at N > 1: the graph lives in HOST memory, sharded by dst rows; every rank pushes its own shard through
-    # the host-buffer entry over its own PCIe link (the src matrix comes from the host on every rank, so this leg needs
-    # no GPU-to-GPU exchange at all).  Time = max over ranks between two barriers; bytes = sum over ranks.
-    e2e_multi = None
-    # (index_scatter's src is edge-aligned: skip the leg when a rank's slice would pin more than 8 GB of host memory)
-    e2e_fits = wk["op"] != "index_scatter" or (E * W * wk["esize"]) / world <= 8e9
-    if world > 1 and e2e_fits:
-        ok, el, moved = 1, 0.0, (0, 0)
-        n_e2e = max(3, min(args.steps, 5))
-        try:
-            tail = list(wk["x"].shape[1:])
-            del out, x_full, plan
-            if ws is not None:
-                del ws
-            pg = blocked = None
-            torch.cuda.empty_cache()
-            if l_E > 0:
-                hx = (h_src_full if h_src_full is not None else l_x_edges.cpu()).pin_memory()
-                hdi = l_di.cpu().pin_memory()
-                hsi = l_si.cpu().pin_memory() if l_si is not None else None
-                hw = l_w.cpu().pin_memory() if l_w is not None else None
-                hout = torch.empty([l_S] + tail, dtype=wk["dtype"]).pin_memory()
-                call = lambda: abi.segment_reduce_host(hx, hsi, hdi, hw, "sum", S=l_S, H=H, weight_layout=layout, out=hout)
-                call()
-        except Exception as ex:      # local failure only (no collective inside): still take part in the reductions below
-            ok = 0
-            print("rank %d: e2e leg failed: %r" % (rank, ex), file=sys.stderr)
-        barrier()
-        t0 = time.perf_counter()
-        try:
-            if ok and l_E > 0:
-                for _ in range(n_e2e):
-                    call()
-                torch.cuda.synchronize()
-                moved = abi.host_last_transfer()
-        except Exception as ex:
-            ok = 0
-            print("rank %d: e2e leg failed: %r" % (rank, ex), file=sys.stderr)
-        barrier()
-        el = (time.perf_counter() - t0) / n_e2e
-        t = torch.tensor([el, float(1 - ok)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        b = torch.tensor([float(moved[0]), float(moved[1])], device=dev, dtype=torch.float64)
-        dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        if t[1].item() == 0:
-            e2e_s = t[0].item()
-            e2e_multi = {"value": round(wk["bytes_logical"] / e2e_s / 1e9, 2), "unit": "GB/s",
-                         "h2d_bytes_per_step": int(b[0].item()), "d2h_bytes_per_step": int(b[1].item()),
-                         "ms_per_step": round(e2e_s * 1e3, 3), "steps": n_e2e, "edges_per_s": E / e2e_s,
-                         "api": "geot_b200_segment_reduce_host on every rank's dst-row shard (host-resident graph, pinned host "
-                                "operands; H2D + kernels + D2H timed between two barriers, max over ranks; bytes summed over ranks)"}
+    traffic = ncu_traffic(wk["name"]) if world == 1 else None
+    _, k_comp, achieved, fr = fractions(wk, r, kmean, peak, traffic)
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "kernel": "geot::segment_reduce_kernel", "kernel_ms": round(kmean, 4),
+                "kernel_share_of_step": round(kmean / ms_per_step, 4), "peak_source": peak_src,
+                "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                "note": "achieved = logical bytes per launch (rank 0's shard at N > 1) / CUDA-event duration of the main kernel "
+                        "alone (events recorded by the library around it; N > 1: both bucket launches of a step, slowest rank).  "
+                        "For gathers the logical bytes include L2-served re-reads of src rows (SURVEY 8d), so `frac` = "
+                        "frac_logical can exceed 1 and is NOT an HBM fraction: frac_dram (ncu dram bytes / kernel time) is what "
+                        "the DRAM interface carried, frac_compulsory what it had to carry at least (%d bytes per launch)" % k_comp}
+    roofline.update(fr)
+    meta = dict(metric=metric_name(wk), dtype=DTYPE_NAME[wk["dtype"]], config=config_of(wk, world, r.exchange), E=wk["E"],
+                launches=r.launches_per_step, exchange=r.exchange, imbalance=r.imbalance, exchanged=r.exchanged)
+
+    n_e2e = max(3, min(args.steps, 5))
+    cpu_obj = None
+    if world > 1:
+        e2e = e2e_multi(r, wk, world, rank, dev, n_e2e)
+        if e2e is None:
+            e2e = {"value": round(value, 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "N > 1: the host-buffer leg was skipped (edge-aligned src too large to pin) or failed on some rank "
+                           "(stderr); this repeats the device-resident value"}
+    else:
+        e2e = e2e_single(r, wk, n_e2e)
+        cpu_obj, _, _ = cpu_arm(wk, 1, 3)
+    del r, wk
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations (every rank takes part at N > 1) ---------------------------------------
+    secondary = {}
+    sec_steps = max(3, min(args.steps, 20))
+    if args.workload == "reddit_gws" and os.environ.get("GEOT_B200_BENCH_SECONDARY", "1") == "1":
+        if world > 1:
+            other = "push" if exchange != "push" else "bucket"
+            for name in ("products_gs64", "products_gs256"):
+                got = run_secondary(name, world, rank, dev, [exchange, other, "replicated"], sec_steps, args.warmup, peak)
+                secondary[name] = {
+                    "inclusive": got[exchange], "inclusive_alt": got[other], "replicated": got["replicated"],
+                    "note": "strong scaling of BASELINE configs[2]; `inclusive` moves the src rows inside the step with the "
+                            "default exchange, `inclusive_alt` with the other overlapped transport, `replicated` is the "
+                            "kernel-scaling number (src pre-replicated, SURVEY 8e)"}
+        else:
+            for name, cpu in (("reddit_index_scatter", False), ("config1_index_scatter", True), ("products_gs64", False),
+                              ("products_gs256", False), ("arxiv_mh_spmm", False)):
+                try:
+                    secondary[name] = run_secondary(name, 1, 0, dev, ["none"], sec_steps, args.warmup, peak, with_cpu=cpu)["none"]
+                except Exception as ex:       # a secondary line must not cost the headline
+                    secondary[name] = {"error": repr(ex)}
+                    torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak_gbs()
-    import workloads as wl
-    k_bytes = wl.bytes_logical(wk["op"], l_E, l_S, N, F, H, wk["esize"])      # per launch (per rank)
-    achieved = k_bytes / (kmean * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "kernel": "geot::segment_reduce_kernel", "kernel_ms": round(kmean, 4),
-                "kernel_share_of_step": round(kmean / ms_per_step, 4), "peak_source": peak_src,
-                "frac_of_nominal_8000": round(achieved / 8000.0, 4),
-                "note": "achieved = logical bytes per launch / CUDA-event duration of the main kernel alone (events recorded by the "
-                        "library around it); for gathers logical bytes include L2-served re-reads of src rows (SURVEY 8d); "
-                        "compulsory DRAM bytes per launch = %d" % wl.bytes_compulsory(wk["op"], l_E, l_S, N, F, H, wk["esize"])}
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and world == 1:       # the ncu captures are of the single-GPU launch
-        try:
-            roofline["traffic"] = json.load(open(tp)).get(wk["name"], {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-    if roofline["traffic"]:
-        # what the DRAM interface itself carried: ncu's bytes per launch over the live launch duration
-        roofline["dram_gbs"] = round(roofline["traffic"] / (kmean * 1e-3) / 1e9, 1)
-        roofline["dram_frac_of_peak"] = round(roofline["dram_gbs"] / peak, 4)
-
-    # ---- e2e: host buffers through the C-ABI host entry (N == 1) -----------------------------------------
-    e2e = None
-    cpu_obj = None
-    if world == 1:
-        hx = wk["x"].cpu().pin_memory(); hdi = l_di.cpu().pin_memory()
-        hsi = l_si.cpu().pin_memory() if l_si is not None else None
-        hw = l_w.cpu().pin_memory() if l_w is not None else None
-        hout = torch.empty(out.shape, dtype=out.dtype).pin_memory()
-        del ws, out
-        torch.cuda.empty_cache()
-        h2d = hx.numel() * hx.element_size() + hdi.numel() * 8 + (hsi.numel() * 8 if hsi is not None else 0) + (
-            hw.numel() * hw.element_size() if hw is not None else 0)
-        d2h = hout.numel() * hout.element_size()
-        n_e2e = max(3, min(args.steps, 5))
-        call = lambda: abi.segment_reduce_host(hx, hsi, hdi, hw, "sum", S=l_S, H=H, weight_layout=layout, out=hout)
-        call()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            call()
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        try:        # what the last call really moved (differs from the operand sizes under GEOT_B200_HOST_COMPACT)
-            h2d, d2h = abi.host_last_transfer()
-        except Exception:
-            pass
-        e2e = {"value": round(wk["bytes_logical"] / e2e_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3), "steps": n_e2e,
-               "transport": {"0": "operands as given", "1": "row pointers instead of dst_index",
-                             "2": "int32 src_index", "3": "row pointers + int32 src_index"}.get(
-                                 os.environ.get("GEOT_B200_HOST_COMPACT", "0"), "operands as given"),
-               "edges_per_s": E / e2e_s,
-               "api": "geot_b200_segment_reduce_host (C ABI, pinned host operands; H2D + kernels + D2H timed, host wall clock)"}
-        cpu_obj, _ = cpu_arm(wk, 1, 3)
-        del hx, hdi, hsi, hw, hout
-    elif e2e_multi is not None:
-        e2e = e2e_multi
-    else:
-        e2e = {"value": round(value, 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "N > 1: the host-buffer leg was skipped (edge-aligned src too large to pin) or failed on some rank "
-                       "(stderr); this repeats the device-resident value"}
-
-    # this library's kernels per step: main + fixup per reduction; pipelined exchange adds the combine and, with
-    # weights, the edge permutation (NCCL's own copy kernels are not counted)
-    launches_per_step = (2 * calls_per_step + ((1 + (1 if l_w is not None else 0)) if pg is not None else 0)
-                         + (1 if exchange in ("needed", "push") else 0))      # + the row pack / push kernel
     line = {
-        "metric": metric_name(wk), "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "metric": meta["metric"], "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": DTYPE_NAME[wk["dtype"]], "data": "synthetic", "config": config_of(wk, world, exchange),
-        "edges_per_s": E / (ms_per_step * 1e-3), "frac_of_measured_hbm": round(value / peak, 4),
+        "vs_baseline": None, "dtype": meta["dtype"], "data": "synthetic", "config": meta["config"],
+        "edges_per_s": meta["E"] / (ms_per_step * 1e-3), "frac_of_measured_hbm": round(value / peak, 4),
         "frac_of_nominal_8000": round(value / 8000.0, 4),
-        "roofline": roofline, "cpu_baseline": cpu_obj, "e2e": e2e,
-        "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "exchange": exchange,
-        "shard_imbalance": round(imbalance, 4),
+        "roofline": roofline, "cpu_baseline": cpu_obj, "e2e": e2e, "parity": parity,
+        "gpu_launches": meta["launches"] * args.steps, "clocks": clocks, "exchange": meta["exchange"],
+        "shard_imbalance": round(meta["imbalance"], 4), "secondary": secondary,
     }
-    if l2_note:
-        line["config"]["l2_persist"] = l2_note
-    if blocked is not None:
-        line["config"]["src_blocks"] = n_blocks
-        line["gpu_launches"] = (2 * n_blocks + 1) * args.steps
-    if exchanged is not None:
-        line["config"]["src_rows_received_per_step_rank0"] = exchanged[0]
-        line["config"]["src_rows_full_exchange_rank0"] = exchanged[1]
+    if meta["exchanged"] is not None:
+        line["config"]["src_rows_received_per_step_rank0"] = meta["exchanged"][0]
+        line["config"]["src_rows_full_exchange_rank0"] = meta["exchanged"][1]
     print(json.dumps(line))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -22,17 +22,25 @@ SYMBOLS = [
     "geot_b200_index_last", "geot_b200_plan_bytes", "geot_b200_format_preprocess", "geot_b200_plan_shards",
     "geot_b200_workspace_bytes", "geot_b200_segment_reduce", "geot_b200_index_scatter",
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
-    "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_combine_partials", "geot_b200_permute_edges",
+    "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_permute_edges",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
     "geot_b200_l2_persist", "geot_b200_l2_persist_reset", "geot_b200_push_rows",
-    "geot_b200_host_last_transfer", "geot_b200_host_row_pointers",
+    "geot_b200_host_last_transfer", "geot_b200_host_row_pointers", "geot_b200_segment_reduce_ex",
+    "geot_b200_host_graph_create", "geot_b200_host_graph_reduce", "geot_b200_host_graph_last_transfer",
+    "geot_b200_host_graph_destroy",
 ]
 
 
 class GeotPlan(ctypes.Structure):
     _fields_ = [("E", ctypes.c_int64), ("S", ctypes.c_int64), ("num_segments", ctypes.c_int64),
                 ("max_degree", ctypes.c_int64), ("is_sorted", ctypes.c_int32), ("has_gaps", ctypes.c_int32),
-                ("rowptr", ctypes.c_void_p)]
+                ("rowptr", ctypes.c_void_p), ("max_row", ctypes.c_int64)]
+
+
+class ReduceOpts(ctypes.Structure):
+    """geot_reduce_opts_t (geot_b200_segment_reduce_ex)."""
+    _fields_ = [("struct_size", ctypes.c_size_t), ("accumulate", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("edge_perm", ctypes.c_void_p), ("mean_rowptr", ctypes.c_void_p)]
 
 
 _lib = None
@@ -58,6 +66,13 @@ def lib() -> ctypes.CDLL:
                                             ctypes.POINTER(ctypes.c_int64), vp]
         L.geot_b200_segment_reduce.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci,
                                                ctypes.POINTER(GeotPlan), vp, sz, vp]
+        L.geot_b200_segment_reduce_ex.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci, ci,
+                                                  ctypes.POINTER(GeotPlan), vp, sz, vp, ctypes.POINTER(ReduceOpts)]
+        L.geot_b200_host_graph_create.argtypes = [vp, vp, i64, i64, i64, ctypes.POINTER(vp)]
+        L.geot_b200_host_graph_reduce.argtypes = [vp, vp, vp, vp, i64, i64, ci, ci, ci]
+        ull = ctypes.POINTER(ctypes.c_ulonglong)
+        L.geot_b200_host_graph_last_transfer.argtypes = [vp, ull, ull, ull]
+        L.geot_b200_host_graph_destroy.argtypes = [vp]
         L.geot_b200_index_scatter.argtypes = [vp, vp, vp, i64, i64, i64, ci, ci, ci, ctypes.POINTER(GeotPlan), vp, sz, vp]
         L.geot_b200_gather_scatter.argtypes = [vp, vp, vp, vp, i64, i64, i64, ci, ci, ctypes.POINTER(GeotPlan), vp, sz, vp]
         L.geot_b200_gather_weight_scatter.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, ci,
@@ -66,7 +81,6 @@ def lib() -> ctypes.CDLL:
                                         ctypes.POINTER(GeotPlan), vp, sz, vp]
         L.geot_b200_sddmm_coo.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, vp]
         L.geot_b200_csr_to_coo.argtypes = [vp, ci, i64, i64, vp, vp]
-        L.geot_b200_combine_partials.argtypes = [vp, ci, i64, vp, i64, i64, ci, ci, vp, vp]
         L.geot_b200_permute_edges.argtypes = [vp, vp, vp, i64, i64, vp]
         L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
         L.geot_b200_l2_persist.argtypes = [vp, sz, vp, ctypes.POINTER(sz), ctypes.POINTER(sz)]
@@ -157,8 +171,10 @@ class Workspace:
 
 
 def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H=1, weight_layout=None,
-                   sorted=True, plan: DevicePlan = None, out=None, workspace: Workspace = None):
-    """Device-pointer call of geot_b200_segment_reduce.  Returns dst [S, W]."""
+                   sorted=True, plan: DevicePlan = None, out=None, workspace: Workspace = None,
+                   accumulate=False, edge_perm=None, mean_rowptr=None):
+    """Device-pointer call of geot_b200_segment_reduce (geot_b200_segment_reduce_ex when one of ``accumulate`` /
+    ``edge_perm`` [E] int32 / ``mean_rowptr`` [S+1] int64 is given).  Returns dst [S, W]."""
     E = dst_index.numel()
     W = src.numel() // src.shape[0]
     F = W // H
@@ -170,10 +186,18 @@ def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H
         out = torch.empty([S] + list(src.shape[1:]), dtype=src.dtype, device=src.device)
     if workspace is None:
         workspace = Workspace(E, W, src.dtype, src.device, sorted)
-    st = lib().geot_b200_segment_reduce(
-        _ptr(src), _ptr(src_index), _ptr(dst_index), _ptr(weight), _ptr(out), E, S, H, F, DTYPE[src.dtype],
-        REDUCE[reduce], weight_layout, 1 if sorted else 0, ctypes.byref(plan.c) if plan is not None else None,
-        _ptr(workspace.buf), workspace.nbytes, _stream())
+    args = (_ptr(src), _ptr(src_index), _ptr(dst_index), _ptr(weight), _ptr(out), E, S, H, F, DTYPE[src.dtype],
+            REDUCE[reduce], weight_layout, 1 if sorted else 0, ctypes.byref(plan.c) if plan is not None else None,
+            _ptr(workspace.buf), workspace.nbytes, _stream())
+    if accumulate or edge_perm is not None or mean_rowptr is not None:
+        assert edge_perm is None or (edge_perm.dtype == torch.int32 and edge_perm.numel() == E)
+        assert mean_rowptr is None or (mean_rowptr.dtype == torch.int64 and mean_rowptr.numel() == S + 1)
+        opts = ReduceOpts(ctypes.sizeof(ReduceOpts), 1 if accumulate else 0, 0,
+                          edge_perm.data_ptr() if edge_perm is not None else None,
+                          mean_rowptr.data_ptr() if mean_rowptr is not None else None)
+        st = lib().geot_b200_segment_reduce_ex(*args, ctypes.byref(opts))
+    else:
+        st = lib().geot_b200_segment_reduce(*args)
     check(st, "segment_reduce")
     return out
 
@@ -192,17 +216,6 @@ def csr_to_coo(rowptr, E):
     out = torch.empty(E, dtype=torch.int64, device=rowptr.device)
     bits = 64 if rowptr.dtype == torch.int64 else 32
     check(lib().geot_b200_csr_to_coo(_ptr(rowptr), bits, rowptr.numel() - 1, E, _ptr(out), _stream()), "csr_to_coo")
-    return out
-
-
-def combine_partials(parts, out, reduce="sum", rowptr=None):
-    """out[S, ...] = sum_k parts[k] (bucket order; / degree for mean) through geot_b200_combine_partials."""
-    n_parts, S = parts.shape[0], parts.shape[1]
-    W = 1
-    for d in parts.shape[2:]:
-        W *= d
-    check(lib().geot_b200_combine_partials(_ptr(parts), n_parts, parts.stride(0), _ptr(out), S, W, DTYPE[parts.dtype],
-                                           REDUCE[reduce], _ptr(rowptr), _stream()), "combine_partials")
     return out
 
 
@@ -254,3 +267,45 @@ def segment_reduce_host(src, src_index, dst_index, weight, reduce="sum", *, S, H
                                             _ptr(out), E, S, H, F, DTYPE[src.dtype], REDUCE[reduce], weight_layout)
     check(st, "segment_reduce_host")
     return out
+
+
+class HostGraph:
+    """Resident host graph (geot_b200_host_graph_*): the index arrays are uploaded once; every ``reduce`` call ships
+    only src (+ weights) and brings dst back.  CPU tensors in, CPU tensor out."""
+
+    def __init__(self, src_index, dst_index, S: int, N_src: int):
+        assert not dst_index.is_cuda and dst_index.dtype == torch.int64 and dst_index.is_contiguous()
+        assert src_index is None or (not src_index.is_cuda and src_index.dtype == torch.int64 and src_index.is_contiguous())
+        self.h = ctypes.c_void_p(0)
+        self.E, self.S, self.N_src = dst_index.numel(), S, N_src
+        check(lib().geot_b200_host_graph_create(_ptr(src_index), _ptr(dst_index), self.E, S, N_src, ctypes.byref(self.h)),
+              "host_graph_create")
+
+    def reduce(self, src, weight=None, reduce="sum", *, H=1, weight_layout=None, out=None):
+        assert not src.is_cuda and src.is_contiguous()
+        W = src.numel() // src.shape[0]
+        if weight_layout is None:
+            weight_layout = W_NONE if weight is None else (W_EDGE if weight.dim() == 1 else W_EDGE_HEAD)
+        if out is None:
+            out = torch.empty([self.S] + list(src.shape[1:]), dtype=src.dtype)
+        check(lib().geot_b200_host_graph_reduce(self.h, _ptr(src), _ptr(weight), _ptr(out), H, W // H, DTYPE[src.dtype],
+                                                REDUCE[reduce], weight_layout), "host_graph_reduce")
+        return out
+
+    def last_transfer(self):
+        """(h2d bytes, d2h bytes) of the last reduce, and the bytes made resident at creation."""
+        a, b, c = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        check(lib().geot_b200_host_graph_last_transfer(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+              "host_graph_last_transfer")
+        return a.value, b.value, c.value
+
+    def close(self):
+        if self.h:
+            lib().geot_b200_host_graph_destroy(self.h)
+            self.h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

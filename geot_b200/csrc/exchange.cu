@@ -1,12 +1,11 @@
 // exchange.cu -- device helpers of the multi-GPU path (geot_b200/dist.py).  New functionality:
 // the reference has no distributed code.
 //
-// The dst-sharded gather ops overlap the exchange of the src row shards with the reduction: a rank's edges are
-// regrouped by the rank that OWNS their src row (stable, so every bucket is still dst-sorted), the bucket of the
-// rank's own rows is reduced while the first peer shard is in flight, bucket k as soon as shard k has landed.
-// Every bucket writes its own partial [S_local, W]; combine_partials adds them in bucket order (a fixed order:
-// results stay bit-reproducible) and applies the mean.  permute_edges carries the per-call edge operands
-// (weights) into bucket order.
+// The dst-sharded gather ops overlap the exchange of the src rows with the reduction: a rank's edges are split once
+// per graph into a src-local and a src-remote bucket (stable, so both stay dst-sorted); the local bucket is reduced
+// while the remote rows travel, the remote bucket afterwards with accumulate (segment_reduce.cuh).  Here:
+// push_rows (the fused pack + transfer over peer memory of the "push" transport) and permute_edges (per-head
+// weights into bucket order; one weight per edge needs no pass: the kernel reads weight[edge_perm[e]]).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -17,65 +16,6 @@
 extern "C" int geot_b200_set_cuda_error(const char *what, int cuda_error);
 
 namespace {
-
-template <typename T> struct Acc { using type = float; };
-template <> struct Acc<double> { using type = double; };
-template <typename T> __device__ __forceinline__ typename Acc<T>::type up(T v) { return v; }
-template <> __device__ __forceinline__ float up<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-template <> __device__ __forceinline__ float up<__half>(__half v) { return __half2float(v); }
-template <typename T> __device__ __forceinline__ T down(typename Acc<T>::type v) { return v; }
-template <> __device__ __forceinline__ __nv_bfloat16 down<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-template <> __device__ __forceinline__ __half down<__half>(float v) { return __float2half_rn(v); }
-
-template <typename T, int V> struct alignas(sizeof(T) * V) Pack { T v[V]; };
-
-// dst[i] = (parts[0][i] + parts[1][i] + ...) [/ degree(row of i)], V elements per thread (V * sizeof(T) == 16 or V == 1)
-template <typename T, int V>
-__global__ void __launch_bounds__(256)
-combine_partials_kernel(const T *__restrict__ parts, int n_parts, int64_t stride, T *__restrict__ dst, int64_t n_vec,
-                        int64_t W, const int64_t *__restrict__ rowptr) {
-  using A = typename Acc<T>::type;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    A a[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) a[k] = A(0);
-    for (int q = 0; q < n_parts; ++q) {
-      const Pack<T, V> x = *reinterpret_cast<const Pack<T, V> *>(parts + (int64_t)q * stride + i * V);
-#pragma unroll
-      for (int k = 0; k < V; ++k) a[k] += up<T>(x.v[k]);
-    }
-    if (rowptr != nullptr) {
-      const int64_t row = (i * V) / W;       // V divides W: a pack never straddles two rows
-      const int64_t deg = rowptr[row + 1] - rowptr[row];
-      if (deg > 1) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) a[k] = a[k] / static_cast<A>(deg);
-      }
-    }
-    Pack<T, V> o;
-#pragma unroll
-    for (int k = 0; k < V; ++k) o.v[k] = down<T>(a[k]);
-    *reinterpret_cast<Pack<T, V> *>(dst + i * V) = o;
-  }
-}
-
-template <typename T>
-cudaError_t combine_launch(const void *parts, int n_parts, int64_t stride, void *dst, int64_t S, int64_t W,
-                           const int64_t *rowptr, cudaStream_t stream) {
-  constexpr int FULL = 16 / (int)sizeof(T);
-  const int64_t n = S * W;
-  const bool vec = (W % FULL == 0) && (stride % FULL == 0) &&
-                   (((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0);
-  const int64_t n_vec = vec ? n / FULL : n;
-  const unsigned blocks = (unsigned)((n_vec + 255) / 256 < 148 * 16 ? (n_vec + 255) / 256 : 148 * 16);
-  if (vec)
-    combine_partials_kernel<T, FULL><<<blocks, 256, 0, stream>>>(static_cast<const T *>(parts), n_parts, stride,
-                                                                static_cast<T *>(dst), n_vec, W, rowptr);
-  else
-    combine_partials_kernel<T, 1><<<blocks, 256, 0, stream>>>(static_cast<const T *>(parts), n_parts, stride,
-                                                             static_cast<T *>(dst), n_vec, W, rowptr);
-  return cudaGetLastError();
-}
 
 // out[e*words + k] = in[perm[e]*words + k]: edge operands (weights) into bucket order, 4-byte words
 __global__ void __launch_bounds__(256)
@@ -131,25 +71,6 @@ push_rows_kernel(const V *__restrict__ x, const int64_t *__restrict__ rows, cons
 
 extern "C" {
 
-int geot_b200_combine_partials(const void *parts, int n_parts, int64_t part_stride, void *dst, int64_t S, int64_t W,
-                               int dtype, int reduce, const int64_t *rowptr, cudaStream_t stream) {
-  if (!parts || !dst || n_parts < 1 || S < 0 || W <= 0 || part_stride < S * W) return GEOT_ERR_INVALID_ARG;
-  if (reduce != GEOT_SUM && reduce != GEOT_MEAN) return GEOT_ERR_UNSUPPORTED;
-  if (reduce == GEOT_MEAN && !rowptr) return GEOT_ERR_INVALID_ARG;
-  if (S == 0) return GEOT_OK;
-  const int64_t *rp = (reduce == GEOT_MEAN) ? rowptr : nullptr;
-  cudaError_t e;
-  switch (dtype) {
-    case GEOT_F32: e = combine_launch<float>(parts, n_parts, part_stride, dst, S, W, rp, stream); break;
-    case GEOT_F64: e = combine_launch<double>(parts, n_parts, part_stride, dst, S, W, rp, stream); break;
-    case GEOT_BF16: e = combine_launch<__nv_bfloat16>(parts, n_parts, part_stride, dst, S, W, rp, stream); break;
-    case GEOT_F16: e = combine_launch<__half>(parts, n_parts, part_stride, dst, S, W, rp, stream); break;
-    default: return GEOT_ERR_INVALID_ARG;
-  }
-  if (e != cudaSuccess) return geot_b200_set_cuda_error("combine_partials_kernel", (int)e);
-  return GEOT_OK;
-}
-
 int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int64_t E, int64_t bytes_per_edge,
                             cudaStream_t stream) {
   if (E < 0 || bytes_per_edge <= 0 || (bytes_per_edge & 1)) return GEOT_ERR_INVALID_ARG;
@@ -178,21 +99,26 @@ int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int6
 
 int geot_b200_push_rows(const void *x, const int64_t *rows, const int32_t *dest_peer, const int64_t *dest_row,
                         void *const *peer_bases, int64_t n, int64_t row_bytes, int peers_aligned16, cudaStream_t stream) {
-  if (n < 0 || row_bytes <= 0 || (row_bytes & 3)) return GEOT_ERR_INVALID_ARG;
+  if (n < 0 || row_bytes <= 0 || (row_bytes & 1)) return GEOT_ERR_INVALID_ARG;
   if (n == 0) return GEOT_OK;
   if (!x || !rows || !dest_peer || !dest_row || !peer_bases) return GEOT_ERR_INVALID_ARG;
-  if (reinterpret_cast<uintptr_t>(x) & 3) return GEOT_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(x) & 1) return GEOT_ERR_INVALID_ARG;
   // the peer bases live in device memory: the caller vouches for their alignment (symmetric allocations are)
   const bool vec16 = row_bytes % 16 == 0 && peers_aligned16 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  const int64_t total = n * (vec16 ? row_bytes / 16 : row_bytes / 4);
+  const bool vec4 = row_bytes % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0;      // (bases: >= 4-byte aligned rows)
+  const int64_t total = n * (vec16 ? row_bytes / 16 : (vec4 ? row_bytes / 4 : row_bytes / 2));
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
   if (vec16)
     push_rows_kernel<uint4><<<blocks, 256, 0, stream>>>(static_cast<const uint4 *>(x), rows, dest_peer, dest_row,
                                                         reinterpret_cast<uint4 *const *>(peer_bases), n, (int)(row_bytes / 16));
-  else
+  else if (vec4)
     push_rows_kernel<uint32_t><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t *>(x), rows, dest_peer, dest_row,
                                                            reinterpret_cast<uint32_t *const *>(peer_bases), n,
                                                            (int)(row_bytes / 4));
+  else      // bf16 / fp16 rows with an odd element count
+    push_rows_kernel<uint16_t><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t *>(x), rows, dest_peer, dest_row,
+                                                           reinterpret_cast<uint16_t *const *>(peer_bases), n,
+                                                           (int)(row_bytes / 2));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return geot_b200_set_cuda_error("push_rows_kernel", (int)e);
   return GEOT_OK;

@@ -55,13 +55,6 @@ template <typename T, int VECW, int LPR, int VPL, int RED, int WM>
 cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
   if constexpr (RED == RED_SUM && VECW * sizeof(T) == 16 && LPR >= 8) {
     int pf = sh.pf;
-    if (pf & kDirectFlag) {     // experiment (GEOT_B200_RING=96): the lean register path, fp32 rows of 256 B - 1 KB
-      if constexpr (WM != WM_GENERIC && sizeof(T) == 4 && sizeof(typename AccOf<T>::type) == 4 && VPL <= 2 && LPR >= 16) {
-        if (p.chunk_edges % LPR == 0)
-          return launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | kDirectFlag>(p, sh, stream);
-      }
-      pf = kLeanFlag | GEOT_LEAN_A;   // not served: the default lean ring
-    }
     if (pf & kLeanFlag) {
       if constexpr (WM != WM_GENERIC && sizeof(typename AccOf<T>::type) == 4) {
         if (p.chunk_edges % LPR == 0) {

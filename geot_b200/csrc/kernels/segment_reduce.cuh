@@ -52,6 +52,16 @@ struct Params {
   int64_t F;                 // per-head width
   int64_t ws_e, ws_h;        // weight element (e,h) at weight[e*ws_e + h*ws_h]
   int mean;                  // 1: divide by the segment length at the end
+  int accumulate;            // 1: dst[row] += result instead of dst[row] = result (sum / mean; later passes of a bucketed
+                             //    reduction: dist.py two-bucket exchange, src-blocked passes)
+  int zero_gaps;             // 1: rows of [fill_lo, fill_hi) that receive no edge are zero-filled by the group that sees
+                             //    the jump in dst_index (replaces a memset of the whole dst)
+  int64_t fill_lo, fill_hi;  // zero_gaps: the rows this call owns (rows left of the first edge's / right of the last
+                             //    edge's row included)
+  const int64_t *mean_rowptr;  // mean over a bucketed reduction: divide by rowptr[row+1] - rowptr[row] (the row's degree
+                             //    in the COMPLETE edge list) instead of by this pass's run length; null: run length
+  const int32_t *edge_perm;  // weight of edge e is weight[edge_perm[e]] (bucketed edge lists keep the caller's weight
+                             //    order); null: weight[e].  One weight per edge only (WM_EDGE)
   int chunk_edges;           // edges per group chunk
   int64_t n_tiles;
   // carries of segments cut by tile boundaries (workspace)
@@ -114,6 +124,11 @@ __device__ __forceinline__ int64_t ld_stream(const int64_t *p, uint64_t pol) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ int32_t ld_stream32(const int32_t *p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
 template <typename T> __device__ __forceinline__ T ld_stream_t(const T *p, uint64_t) { return __ldg(p); }
 template <> __device__ __forceinline__ float ld_stream_t<float>(const float *p, uint64_t pol) {
   float v;
@@ -152,26 +167,22 @@ constexpr int kTmaFlag = 16;
 //            instructions per 512-byte row instead of 32 (profiles/r01c_*).  sum kernels with fp32 accumulators,
 //            no per-head weights, chunks that are whole batches.
 constexpr int kLeanFlag = 32;
-//   PF & 64 (kDirectFlag, with kLeanFlag; experiment, GEOT_B200_RING=96): the LEAN REGISTER path -- the lean
-//            bookkeeping (ids / weights parked in shared memory, position-based run lengths) with the rows loaded
-//            straight into two register buffers of U rows (one consumed while the next is in flight), so a gathered
-//            byte crosses the L1TEX data pipe once instead of twice (LDGSTS in + LDS out: 84 % busy on Reddit gws).
-constexpr int kDirectFlag = 64;
+//   (A "lean register path" -- the same bookkeeping with the rows loaded straight into double-buffered registers, so
+//   that a gathered byte crosses the L1TEX data pipe once -- was built and measured in round 2: 15-25 % SLOWER than the
+//   ring on every gather workload, profiles/r02a_ring96_ab.txt; too few bytes in flight per SM.  Removed.)
 template <typename T, int VECW, int LPR, int VPL, int PF_>
 struct ShapeOf {
   using A = typename AccOf<T>::type;
   static constexpr bool TMA = (PF_ & kTmaFlag) != 0;
-  static constexpr bool DIRECT = (PF_ & kDirectFlag) != 0;
-  static constexpr bool LEAN = (PF_ & kLeanFlag) != 0 && !DIRECT;   // the lean RING
-  static constexpr int PF = DIRECT ? 0 : (PF_ & (kTmaFlag - 1));   // ring depth
+  static constexpr bool LEAN = (PF_ & kLeanFlag) != 0;   // the lean ring
+  static constexpr int PF = PF_ & (kTmaFlag - 1);       // ring depth
   static constexpr int NG = kThreads / LPR;      // chunks (groups) per tile
   static constexpr int CW = LPR * VPL * VECW;    // columns per CTA
   // ring: 4 rows per sub-batch (2 for the widest rows) measured best on B200 (profiles/r01_ring_sweep.md)
   static constexpr int RU = GEOT_RING_U > 0 ? (GEOT_RING_U / VPL > 0 ? GEOT_RING_U / VPL : 1) : (VPL >= 4 ? 2 : 4);
   // lean ring: 2 KB of rows per warp and stage, at least 4 sub-batches per batch
   static constexpr int LU = (VPL >= 4) ? 1 : (VPL == 2 ? 2 : (LPR >= 16 ? 4 : (LPR >= 8 ? 2 : 1)));
-  static constexpr int DU = (VPL >= 2) ? 4 : 8;   // lean register path: two buffers of DU rows = 64 data registers
-  static constexpr int U0 = DIRECT ? DU : (LEAN ? LU : (PF > 0 ? RU : ((VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0))));
+  static constexpr int U0 = LEAN ? LU : (PF > 0 ? RU : ((VPL >= 4) ? 2 : (VPL == 2 ? 4 : GEOT_U0)));
   static constexpr int U = (LPR < U0) ? LPR : U0;   // rows per sub-batch
   static constexpr int NS = PF + 1;              // ring stages
   static constexpr int SB = LPR / U;             // sub-batches per batch
@@ -180,16 +191,14 @@ struct ShapeOf {
   static constexpr size_t scalars_off = (LEAN ? 1 : 2) * (size_t)NG * CW * sizeof(A);
   static constexpr size_t carry_bytes = ((scalars_off + (size_t)NG * (4 * 8 + 4)) + 127) & ~(size_t)127;
   // lean: per group two operand buffers of LPR src row ids + LPR weights
-  static constexpr size_t ops_bytes = (LEAN || DIRECT) ? (size_t)NG * 4 * LPR * 4 : 0;
+  static constexpr size_t ops_bytes = LEAN ? (size_t)NG * 4 * LPR * 4 : 0;
   static constexpr size_t ring_off = carry_bytes + ops_bytes;
   static constexpr size_t ring_bytes = PF > 0 ? (size_t)NG * NS * U * CW * sizeof(T) : 0;
   static constexpr size_t bar_bytes = TMA ? (((size_t)NG * NS * 8 + 127) & ~(size_t)127) : 0;   // one mbarrier per (group, stage)
   static constexpr size_t smem_bytes = ring_off + ring_bytes + bar_bytes;
   static constexpr int max_blocks = (int)((227 * 1024) / (smem_bytes + 1024));
   static constexpr int min_blocks_direct = (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1));
-  static constexpr int min_blocks = DIRECT ? 2 : (PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1)));
-  static_assert(!DIRECT || (VPL <= 2 && SB % 2 == 0 && sizeof(A) == 4 && VECW * sizeof(T) == 16),
-                "lean register path: an even number of sub-batches per batch, fp32 accumulators, 16-byte vectors");
+  static constexpr int min_blocks = PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1));
   static_assert(PF == 0 || LEAN || PF * U <= LPR, "the prefetch distance must stay within one batch ahead");
   static_assert(!LEAN || (PF > 0 && SB % NS == 0 && sizeof(A) == 4 && U * sizeof(T) >= sizeof(A)),
                 "lean ring: the stages must divide the batch; fp32 accumulators; a stage holds a carry row");
@@ -238,13 +247,12 @@ segment_reduce_kernel(const Params p) {
   constexpr int PF = SH::PF;
   constexpr bool TMA = SH::TMA;
   constexpr bool LEAN = SH::LEAN;
-  constexpr bool DIRECT = SH::DIRECT;
   constexpr int NG = SH::NG;      // chunks per tile
   constexpr int CW = SH::CW;      // columns per CTA
   constexpr int U = SH::U;        // row loads in flight per group (PF == 0) / rows per ring sub-batch
   constexpr int NS = SH::NS;
   static_assert(PF == 0 || VECW * sizeof(T) == 16, "the ring moves 16-byte pieces");
-  static_assert(!(LEAN || DIRECT) || (RED == RED_SUM && WM != WM_GENERIC), "lean paths: sum, at most one weight per edge");
+  static_assert(!LEAN || (RED == RED_SUM && WM != WM_GENERIC), "lean ring: sum, at most one weight per edge");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A *s_head = reinterpret_cast<A *>(smem_raw);              // [NG][CW]
@@ -341,17 +349,32 @@ segment_reduce_kernel(const Params p) {
   };
 
   auto finalize_store = [&](int64_t row, A(&a)[VPL][VECW], long long n) {
+    if (p.mean && p.mean_rowptr != nullptr) n = p.mean_rowptr[row + 1] - p.mean_rowptr[row];
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       if (!col_ok[j]) continue;
+      VecT *q = reinterpret_cast<VecT *>(dst + row * W + col[j]);
       VecT out;
+      if (p.accumulate) out = *q;
 #pragma unroll
       for (int i = 0; i < VECW; ++i) {
         A v = a[j][i];
         if (p.mean) v = v / static_cast<A>(n);
+        if (p.accumulate) v = to_acc<T>(out.v[i]) + v;
         out.v[i] = from_acc<T>(v);
       }
-      *reinterpret_cast<VecT *>(dst + row * W + col[j]) = out;
+      *q = out;
+    }
+  };
+  // rows [lo, hi) receive no edge: they read 0 (zero_gaps; a cold path -- the jump in dst_index is seen by one group)
+  auto fill_gap = [&](int64_t lo, int64_t hi) {
+    VecT z;
+#pragma unroll
+    for (int i = 0; i < VECW; ++i) z.v[i] = from_acc<T>(A(0));
+    for (int64_t r = lo; r < hi; ++r) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+        if (col_ok[j]) *reinterpret_cast<VecT *>(dst + r * W + col[j]) = z;
     }
   };
 
@@ -360,9 +383,14 @@ segment_reduce_kernel(const Params p) {
     const int64_t next_row = (e_end < E) ? dst_index[e_end] : -1;
     int64_t last_dst = dst_index[e_begin];   // dst of the edge left of the current batch
     bool is_head = (last_dst == prev_row);   // the open run entered the chunk from the left
+    if (p.zero_gaps) {
+      const int64_t left_row = (e_begin > 0) ? prev_row : p.fill_lo - 1;
+      if (last_dst > left_row + 1) fill_gap(left_row + 1, last_dst);
+    }
 
-    // closes the open run, whose row is `row`
-    auto close_run = [&](int64_t row) {
+    // closes the open run, whose row is `row`; the run that starts has row `next`
+    auto close_run = [&](int64_t row, int64_t next) {
+      if (p.zero_gaps && next > row + 1) fill_gap(row + 1, next);
       if (is_head) {
         park(s_head + g * CW, s_head_cnt, s_head_row, row);
         flags |= FLAG_HEAD;
@@ -388,146 +416,7 @@ segment_reduce_kernel(const Params p) {
         }
     };
 
-    if constexpr (DIRECT) {
-      // ---- lean register path (see ShapeOf; experiment) ----------------------------------------------------
-      constexpr int SB = SH::SB;                   // sub-batches per batch (even)
-      constexpr int RING_WORDS = 2 * LPR;          // operand buffers: two batches, circular
-      const int n_edges = (int)(e_end - e_begin);
-      const int nfull = n_edges / LPR;             // whole batches; a remainder only in the edge list's last chunk
-      const int n_ring = nfull * LPR;              // edges that take the batched path
-      uint32_t *ids = reinterpret_cast<uint32_t *>(smem_raw + SH::carry_bytes) + g * (2 * RING_WORDS);   // src row ids
-      float *wts = reinterpret_cast<float *>(ids + RING_WORDS);                                          // weights
-      const uint32_t row_bytes32 = (uint32_t)p.W * (uint32_t)sizeof(T);
-      uint32_t ld32 = (uint32_t)last_dst;          // dst row of the edge left of the current batch
-
-      auto ld_ops = [&](int bi, uint32_t &d, uint32_t &sid, float &wv) {
-        const int64_t e = e_begin + (int64_t)bi * LPR + gl;
-        d = (uint32_t)ld_stream(dst_index + e, pol);
-        sid = src_index ? (uint32_t)ld_stream(src_index + e, pol) : (uint32_t)e;
-        wv = 1.f;
-        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + e, pol));
-      };
-      // loads the U rows whose ids are at o[0..U) into a register buffer (L2-only caching, like the ring's cp.async.cg)
-      auto fetch = [&](const uint32_t *o, VecT(&v)[U][VPL]) {
-        const Vec<uint32_t, U> r = *reinterpret_cast<const Vec<uint32_t, U> *>(o);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-#pragma unroll
-          for (int j = 0; j < VPL; ++j) {
-            const uint4 t = __ldcg(reinterpret_cast<const uint4 *>(row_addr(lane_src[j], r.v[u], row_bytes32)));
-            v[u][j] = *reinterpret_cast<const VecT *>(&t);
-          }
-        }
-      };
-      auto add_edge = [&](const VecT(&v)[VPL], float we) {
-#pragma unroll
-        for (int j = 0; j < VPL; ++j)
-#pragma unroll
-          for (int i = 0; i < VECW; ++i) {
-            float x = to_acc<T>(v[j].v[i]);
-            if (WM != WM_NONE) x = x * we;
-            acc[j][i] = acc[j][i] + x;
-          }
-      };
-
-      uint32_t d_cur = 0, d_nxt = 0, l_d = 0, l_s = 0;
-      float l_w = 1.f;
-      if (nfull > 0) {
-        ld_ops(0, d_cur, l_s, l_w);
-        ids[gl] = l_s;
-        wts[gl] = l_w;
-      }
-      if (nfull > 1) {
-        ld_ops(1, d_nxt, l_s, l_w);
-        ids[LPR + gl] = l_s;
-        wts[LPR + gl] = l_w;
-      }
-      __syncwarp(gmask);
-      VecT va[U][VPL], vb[U][VPL];                 // the sub-batch being consumed / the one in flight
-      if (nfull > 0) fetch(ids, va);
-      int pos = 0;          // chunk-relative position of the current pair of sub-batches
-      int run_start = 0;    // chunk-relative position where the open run began
-      int slot = 0;         // word offset of the current batch in the operand buffers: 0 or LPR
-      unsigned bmask = 0;
-      uint32_t batch_left = 0;
-      int batch_pos = 0;
-
-      // consumes sub-batch `t` (0 or 1) of the current pair from `v`, after putting the next one in flight into `vn`
-      auto step = [&](int t, int blk, VecT(&v)[U][VPL], VecT(&vn)[U][VPL]) {
-        const int c = (t + 1) * U;                                     // distance of the next sub-batch from `pos`
-        if (pos + c < n_ring) fetch(ids + ((blk + c) & (RING_WORDS - 1)), vn);
-        Vec<float, U> wv;
-#pragma unroll
-        for (int u = 0; u < U; ++u) wv.v[u] = 1.f;
-        if (WM == WM_EDGE) wv = *reinterpret_cast<const Vec<float, U> *>(wts + blk + t * U);
-        const unsigned sub = bmask & low_bits<U>();
-        bmask >>= U;
-        if (sub == 0) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) add_edge(v[u], wv.v[u]);
-        } else {
-          // a dst row starts inside these U edges (register buffers: the loop over u must stay unrolled)
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if ((sub >> u) & 1u) {
-              const int k = pos + t * U + u;            // chunk-relative position of this edge
-              const int kb = k - batch_pos;             // position inside the batch
-              const uint32_t row = __shfl_sync(gmask, d_cur, kb > 0 ? kb - 1 : 0, LPR);
-              cnt = k - run_start;
-              close_run((int64_t)(kb > 0 ? row : batch_left));
-              run_start = k;
-            }
-            add_edge(v[u], wv.v[u]);
-          }
-        }
-      };
-
-#pragma unroll 1
-      for (int bi = 0; bi < nfull; ++bi) {
-        const bool has_nn = bi + 2 < nfull;
-        if (has_nn) ld_ops(bi + 2, l_d, l_s, l_w);     // parked at the end of this batch, used from the next one on
-        uint32_t left = __shfl_up_sync(gmask, d_cur, 1, LPR);
-        if (gl == 0) left = ld32;
-        bmask = (__ballot_sync(gmask, d_cur != left) >> gshift) & low_bits<LPR>();
-        batch_left = ld32;
-        ld32 = __shfl_sync(gmask, d_cur, LPR - 1, LPR);
-        batch_pos = pos;
-#pragma unroll 1
-        for (int s0 = 0; s0 < SB; s0 += 2) {
-          const int blk = slot + s0 * U;
-          step(0, blk, va, vb);
-          step(1, blk, vb, va);
-          pos += 2 * U;
-        }
-        // this batch's operand buffer is free: park batch bi+2 there
-        __syncwarp(gmask);
-        if (has_nn) {
-          ids[slot + gl] = l_s;
-          wts[slot + gl] = l_w;
-        }
-        __syncwarp(gmask);
-        slot ^= LPR;
-        d_cur = d_nxt;
-        d_nxt = l_d;
-      }
-      cnt = pos - run_start;
-      // remainder of the edge list's last chunk: one edge at a time, uniform operand loads
-      for (int k = pos; k < n_edges; ++k) {
-        const int64_t e = e_begin + k;
-        const uint32_t d = (uint32_t)dst_index[e];
-        const int64_t sid = src_index ? src_index[e] : e;
-        float we = 1.f;
-        if (WM == WM_EDGE) we = to_acc<T>(weight[e]);
-        VecT v[VPL];
-#pragma unroll
-        for (int j = 0; j < VPL; ++j) v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + sid * row_bytes);
-        if (d != ld32) close_run((int64_t)ld32);
-        add_edge(v, we);
-        ++cnt;
-        ld32 = d;
-      }
-      last_dst = (int64_t)ld32;
-    } else if constexpr (LEAN) {
+    if constexpr (LEAN) {
       // ---- lean ring (see ShapeOf) ---------------------------------------------------------------------
       constexpr int SB = SH::SB;                   // sub-batches per batch; NS | SB
       constexpr int RING_WORDS = 2 * LPR;          // operand buffers: two batches, circular
@@ -545,7 +434,7 @@ segment_reduce_kernel(const Params p) {
         d = (uint32_t)ld_stream(dst_index + e, pol);
         sid = src_index ? (uint32_t)ld_stream(src_index + e, pol) : (uint32_t)e;
         wv = 1.f;
-        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + e, pol));
+        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + (p.edge_perm ? (int64_t)ld_stream32(p.edge_perm + e, pol) : e), pol));
       };
       // copies the U rows whose ids are at o[0..U) into ring stage st (compile-time)
       auto issue = [&](const uint32_t *o, int st) {
@@ -637,8 +526,9 @@ segment_reduce_kernel(const Params p) {
                 if ((sub >> u) & 1u) {
                   const int kb = k - batch_pos;           // position inside the batch
                   const uint32_t row = __shfl_sync(gmask, d_cur, kb > 0 ? kb - 1 : 0, LPR);
+                  const uint32_t nxt = __shfl_sync(gmask, d_cur, kb, LPR);
                   cnt = k - run_start;
-                  close_run((int64_t)(kb > 0 ? row : batch_left));
+                  close_run((int64_t)(kb > 0 ? row : batch_left), (int64_t)nxt);
                   run_start = k;
                 }
                 VecT vv[VPL];
@@ -670,11 +560,11 @@ segment_reduce_kernel(const Params p) {
         const uint32_t d = (uint32_t)dst_index[e];
         const int64_t sid = src_index ? src_index[e] : e;
         float we = 1.f;
-        if (WM == WM_EDGE) we = to_acc<T>(weight[e]);
+        if (WM == WM_EDGE) we = to_acc<T>(weight[p.edge_perm ? (int64_t)p.edge_perm[e] : e]);
         VecT v[VPL];
 #pragma unroll
         for (int j = 0; j < VPL; ++j) v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + sid * row_bytes);
-        if (d != ld32) close_run((int64_t)ld32);
+        if (d != ld32) close_run((int64_t)ld32, (int64_t)d);
         add_edge(v, we);
         ++cnt;
         ld32 = d;
@@ -689,7 +579,7 @@ segment_reduce_kernel(const Params p) {
         const int64_t s = valid ? (src_index ? ld_stream(src_index + my_e, pol) : my_e) : 0;
         my_off = s * row_bytes;
         my_w = A(1);
-        if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + my_e, pol));
+        if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + (p.edge_perm ? (int64_t)ld_stream32(p.edge_perm + my_e, pol) : my_e), pol));
       };
 
       // operands of the current batch (my_*) and of the next one (n_*); the one after that is loaded at the
@@ -810,7 +700,7 @@ segment_reduce_kernel(const Params p) {
                 if ((sub >> u) & 1u) {
                   const int k = k0 + u;
                   const int64_t row = (k == 0) ? batch_left : __shfl_sync(gmask, my_dst, (k == 0) ? 0 : k - 1, LPR);
-                  close_run(row);
+                  close_run(row, __shfl_sync(gmask, my_dst, k, LPR));
                 }
                 accumulate(v[u], w[u]);
                 ++cnt;
@@ -831,7 +721,7 @@ segment_reduce_kernel(const Params p) {
               w[j] = we;
               if (WM == WM_GENERIC && wb[j] != nullptr) w[j] = to_acc<T>(__ldg(wb[j] + k * ws_e32));
             }
-            if ((bmask >> k) & 1u) close_run(k == 0 ? batch_left : row);
+            if ((bmask >> k) & 1u) close_run(k == 0 ? batch_left : row, __shfl_sync(gmask, my_dst, k, LPR));
             accumulate(v, w);
             ++cnt;
           }
@@ -843,6 +733,7 @@ segment_reduce_kernel(const Params p) {
 
     // the run still open at the chunk end
     const int64_t cur_row = last_dst;
+    if (p.zero_gaps && e_end == E && p.fill_hi > cur_row + 1) fill_gap(cur_row + 1, p.fill_hi);
     const bool continues = (cur_row == next_row);
     if (is_head) {                      // the whole chunk is one run that entered from the left
       park(s_head + g * CW, s_head_cnt, s_head_row, cur_row);
@@ -954,6 +845,7 @@ segment_fixup_kernel(const Params p) {
   if (has && !is_long) {
     long long n = p.tail_cnt[t];
     for (int64_t j = t + 1; j <= last; ++j) n += p.head_cnt[j];
+    if (p.mean && p.mean_rowptr != nullptr) n = p.mean_rowptr[p.tail_row[t] + 1] - p.mean_rowptr[p.tail_row[t]];
     const A *tail = static_cast<const A *>(p.carry_tail) + t * W;
     T *dst = static_cast<T *>(p.dst) + p.tail_row[t] * W;
     for (int64_t c = lane; c < W; c += 32) {
@@ -965,6 +857,7 @@ segment_fixup_kernel(const Params p) {
       }
       for (; j <= last; ++j) a = red_op<RED, A>(a, head[j * W + c]);
       if (p.mean) a = a / static_cast<A>(n);
+      if (p.accumulate) a = to_acc<T>(dst[c]) + a;
       dst[c] = from_acc<T>(a);
     }
   }
@@ -978,6 +871,7 @@ segment_fixup_kernel(const Params p) {
     for (int64_t j = tt + 1 + lane; j <= lst; j += 32) n += p.head_cnt[j];
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     n += p.tail_cnt[tt];
+    if (p.mean && p.mean_rowptr != nullptr) n = p.mean_rowptr[p.tail_row[tt] + 1] - p.mean_rowptr[p.tail_row[tt]];
     for (int64_t c0 = 0; c0 < W; c0 += 32) {
       const int64_t c = c0 + lane;
       A a = red_identity<RED, A>();
@@ -996,7 +890,9 @@ segment_fixup_kernel(const Params p) {
 #pragma unroll
         for (int k = 0; k < NW; ++k) r = red_op<RED, A>(r, s_part[k * 32 + lane]);
         if (p.mean) r = r / static_cast<A>(n);
-        (static_cast<T *>(p.dst) + p.tail_row[tt] * W)[c] = from_acc<T>(r);
+        T *q = static_cast<T *>(p.dst) + p.tail_row[tt] * W + c;
+        if (p.accumulate) r = to_acc<T>(*q) + r;
+        *q = from_acc<T>(r);
       }
       __syncthreads();
     }

@@ -5,30 +5,23 @@ One process per GPU (``torch.distributed``, NCCL over NVLink / NVSwitch).  The d
 cut into ``world_size`` contiguous dst-row ranges with balanced edge counts; rank g owns rows
 ``[row_bounds[g], row_bounds[g+1])`` of every node-feature matrix and the edges that point into them,
 reduces its own dst slice, and writes only that slice -- there is no reduction collective.  The only
-exchange is the all-gather of the src feature rows that gather ops read across shard boundaries.
+exchange is that of the src feature rows that gather ops read across shard boundaries.
 ``index_scatter`` needs no communication at all (edge-aligned data is sharded with the edges).
 
-Two forms of the exchange:
+Forms of the exchange:
 
-* ``all_gather_rows`` + one reduction (``sharded_gather_scatter``): the whole matrix lands, then the kernel runs.
-* ``PipelinedGather``: the all-gather is unrolled into ``world-1`` staggered NCCL send/recv steps (step k: send my
-  rows to rank r-k, receive the rows of rank r+k -- every rank sends and receives exactly one shard per step, so
-  each step runs at full NVSwitch bandwidth) on a side stream, and the rank's edges are regrouped by the rank that
-  owns their src row: the bucket of the rank's own rows is reduced while shard r+1 is in flight, bucket r+k as soon
-  as step k has landed.  Buckets write partial results that one combine kernel adds in bucket order (fixed order:
-  bit-reproducible), so the exchange costs what exceeds the reduction time instead of adding to it.
-* ``PipelinedGather(needed_only=True)``: the same schedule, but step k carries only the rows the receiver's edges
-  actually reference (SURVEY 8e "exchanging only the rows actually referenced").  The request lists are exchanged
-  once per graph; every call packs the requested rows per peer (one row-gather kernel) and the receiver's bucket k
-  reads them from a compact buffer through remapped src ids.  Pays off when a shard references a fraction of a
-  peer's rows (sparse, products-like graphs); on dense graphs (Reddit: every shard references almost every row)
-  it degenerates to the full exchange plus the pack.
-* ``PeerPushGather``: the needed-rows exchange without NCCL on the data path.  Every rank's receive buffer is a
-  symmetric-memory allocation mapped into all processes of the box; ONE kernel per call packs the requested rows
-  and stores each straight into its slot of the requester's buffer over NVLink (``geot_b200_push_rows``), between
-  two cross-GPU barriers on a side stream, while the main stream reduces the edges whose src rows are local; the
-  remote edges are reduced when the barrier has passed, and a two-way combine finishes.  Two buckets instead of
-  ``world``: 2 reductions + 1 push + 1 combine per call whatever the GPU count.
+* ``sharded_gather_scatter``: one ragged all-gather, then one reduction (also serves max / min).
+* ``BucketedGather`` (sum / mean): the rank's edges are split ONCE per graph, stably, into two dst-sorted buckets --
+  src row local / src row remote.  Per call the remote rows travel on a side stream while the main stream reduces the
+  local bucket (writing every row of the output, rows without local edges as zeros); when the rows have landed the
+  remote bucket is reduced with ``accumulate`` (``dst += partial``, ``geot_b200_segment_reduce_ex``).  The host cost
+  is the same whatever the GPU count: 1 exchange + 2 reductions, no combine pass, no per-call weight permutation
+  (the kernel reads ``weight[edge_perm[e]]``).  Two transports:
+
+  - ``"allgather"``: one ragged NCCL all-gather into the ``[N, ...]`` replica buffer;
+  - ``"push"``: only the rows a peer's edges actually reference, stored by ONE kernel straight into the requesters'
+    symmetric-memory buffers over NVLink (``geot_b200_push_rows``: P2P stores, no NCCL on the data path) between two
+    cross-GPU barriers.  Pays off when a shard references a fraction of a peer's rows (products-like graphs).
 """
 from dataclasses import dataclass
 from typing import List, Optional
@@ -163,72 +156,72 @@ def sharded_index_scatter(shard: GraphShard, src_local_edges: torch.Tensor, redu
     return _pad_rows(out, shard.num_local_rows)
 
 
-# ---- exchange overlapped with the reduction -------------------------------------------------------
+# ---- exchange overlapped with the reduction: two edge buckets ---------------------------------------
 
 @dataclass
 class SrcBuckets:
-    """A rank's edges regrouped by the owner of their src row, in processing order: bucket k holds the edges whose
-    src row belongs to rank ``(rank + k) % world`` (bucket 0 = the rank's own rows).  The regrouping is stable, so
-    every bucket is still sorted by dst."""
-    perm: torch.Tensor               # [E_local] position in the shard's edge list of every regrouped edge
-    bounds: List[int]                # world+1 offsets of the buckets in the regrouped arrays
-    src_index: torch.Tensor          # [E_local] regrouped
-    dst_index: torch.Tensor          # [E_local] regrouped (local dst rows)
-
-
-def bucket_by_src_owner(shard: GraphShard) -> SrcBuckets:
-    world, rank = shard.world_size, shard.rank
-    cuts = torch.tensor(shard.row_bounds[1:-1], dtype=shard.src_index.dtype, device=shard.src_index.device)
-    owner = torch.bucketize(shard.src_index, cuts, right=True)          # rb[g] <= s < rb[g+1]  <=>  owner == g
-    key = (owner - rank) % world
-    perm = torch.argsort(key, stable=True)
-    counts = torch.bincount(key, minlength=world).tolist()
-    bounds = [0]
-    for c in counts:
-        bounds.append(bounds[-1] + int(c))
-    return SrcBuckets(perm, bounds, shard.src_index[perm].contiguous(), shard.dst_index[perm].contiguous())
+    """A rank's edges split stably by where their src row lives: bucket 0 = the rank's own rows, bucket 1 = rows of
+    the other ranks.  Both stay sorted by dst.  ``perm[e]`` is the position of bucketed edge e in the shard's edge
+    list (int32: what the kernel indexes the caller's weights with)."""
+    perm: torch.Tensor               # [E_local] int32
+    bounds: List[int]                # [0, n_local_src, E_local]
+    src_index: torch.Tensor          # [E_local] int64: bucket 0 -> LOCAL row ids (into the rank's own rows);
+                                     #                  bucket 1 -> ids into the buffer the transport fills
+    dst_index: torch.Tensor          # [E_local] int64 local dst rows
 
 
 @dataclass
 class NeededRows:
-    """Per-graph state of the needed-rows exchange (``PipelinedGather(needed_only=True)``)."""
+    """Per-graph state of the needed-rows ("push") transport."""
     recv_counts: List[int]           # [world] rows this rank receives from each owner (0 for itself)
-    recv_offsets: List[int]          # [world+1] their offsets in the compact receive buffer, in STEP order (rank+1, rank+2, ...)
+    recv_offsets: List[int]          # [world+1] their offsets in the receive buffer, in STEP order (rank+1, rank+2, ...)
     send_counts: List[int]           # [world] rows each peer asked this rank for
-    send_offsets: List[int]          # [world+1] their offsets in the packed send buffer, in STEP order (rank-1, rank-2, ...)
-    send_rows: torch.Tensor          # [sum(send_counts)] LOCAL row ids to pack, grouped by peer in step order
-    src_index: torch.Tensor          # [E_local] bucket-ordered src ids: bucket 0 -> local row ids, bucket k -> row ids
-                                     #           in the compact receive buffer
+    send_rows: torch.Tensor          # [sum(send_counts)] LOCAL row ids to push, grouped by peer in step order
+    dest_peer: torch.Tensor          # [sum(send_counts)] int32: the peer every pushed row goes to
+    dest_row: torch.Tensor           # [sum(send_counts)] int64: its slot in that peer's receive buffer
+    buffer_rows: int                 # rows of the (symmetric: same size everywhere) receive buffer
 
 
-def build_needed_rows(shard: GraphShard, buckets: SrcBuckets, group=None) -> NeededRows:
-    """One-time request exchange: for every peer the sorted unique rows this rank's edges reference there.
+def split_local_remote(shard: GraphShard):
+    """(perm [E] int64, n_local): stable split of the shard's edges into src-local first, src-remote second."""
+    rb, rank = shard.row_bounds, shard.rank
+    s = shard.src_index
+    remote = ((s < rb[rank]) | (s >= rb[rank + 1])).to(torch.int8)
+    perm = torch.argsort(remote, stable=True)
+    n_local = int(s.numel() - int(remote.sum()))
+    return perm, n_local
 
-    Collectives: one all-gather of the [world] request counts, then ``world-1`` staggered send/recv steps of the
-    request lists (the same schedule the row exchange uses: works on NCCL and gloo alike)."""
+
+def build_needed_rows(shard: GraphShard, remote_src: torch.Tensor, group=None):
+    """One-time request exchange of the push transport.  ``remote_src``: the global src ids of the rank's remote-src
+    edges.  Returns (NeededRows, compact ids of those edges into the receive buffer).
+
+    Collectives: one all-gather of the [world] request counts and offsets, then ``world-1`` staggered send/recv steps
+    of the request lists (works on NCCL and gloo alike)."""
     world, rank, rb = shard.world_size, shard.rank, shard.row_bounds
-    dev, idt = buckets.src_index.device, buckets.src_index.dtype
-    b = buckets.bounds
-    src = torch.empty_like(buckets.src_index)
-    src[b[0]:b[1]] = buckets.src_index[b[0]:b[1]] - rb[rank]
+    dev, idt = remote_src.device, remote_src.dtype
+    cuts = torch.tensor(rb[1:-1], dtype=idt, device=dev)
+    owner = torch.bucketize(remote_src, cuts, right=True) if world > 1 else torch.zeros_like(remote_src)
+    compact = torch.empty_like(remote_src)
     need, recv_counts, recv_offsets = {}, [0] * world, [0]
     for k in range(1, world):                       # step order: owner rank+k
         g = (rank + k) % world
-        s_k = buckets.src_index[b[k]:b[k + 1]]
+        sel = owner == g
+        s_k = remote_src[sel]
         uniq = torch.unique(s_k)                    # sorted
         need[g] = (uniq - rb[g]).contiguous()       # as the owner's local row ids
         recv_counts[g] = int(uniq.numel())
-        src[b[k]:b[k + 1]] = recv_offsets[-1] + torch.searchsorted(uniq, s_k)
+        compact[sel] = recv_offsets[-1] + torch.searchsorted(uniq, s_k)
         recv_offsets.append(recv_offsets[-1] + recv_counts[g])
-    recv_offsets.append(recv_offsets[-1])           # world+1 entries (last step has no successor)
-    # counts[r][g] = rows rank r needs from rank g
-    mine = torch.tensor(recv_counts, dtype=torch.int64, device=dev)
-    counts = torch.empty(world * world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts, mine, group=group)
-    counts = counts.view(world, world).cpu()
-    send_counts = [int(counts[g][rank]) for g in range(world)]
+    recv_offsets.append(recv_offsets[-1])           # world+1 entries
+    # table[r] = rank r's (recv_counts by owner, recv_offsets by step)
+    mine = torch.tensor(recv_counts + recv_offsets, dtype=torch.int64, device=dev)
+    table = torch.empty(world * (2 * world + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(table, mine, group=group)
+    table = table.view(world, 2 * world + 1).cpu()
+    send_counts = [int(table[g][rank]) for g in range(world)]
     send_counts[rank] = 0
-    send_offsets, lists = [0], []
+    lists, peers, slots = [], [], []
     for k in range(1, world):                       # step order: I serve rank-k in step k
         to, frm = (rank - k) % world, (rank + k) % world
         lst = torch.empty(send_counts[to], dtype=idt, device=dev)
@@ -241,249 +234,127 @@ def build_needed_rows(shard: GraphShard, buckets: SrcBuckets, group=None) -> Nee
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
         lists.append(lst)
-        send_offsets.append(send_offsets[-1] + send_counts[to])
-    send_offsets.append(send_offsets[-1])
+        # my rows for `to` land at the offset of ITS step k (owner = me) in its receive buffer
+        n = send_counts[to]
+        peers.append(torch.full((n,), to, dtype=torch.int32))
+        slots.append(int(table[to][world + k - 1]) + torch.arange(n, dtype=torch.int64))
     send_rows = torch.cat(lists) if lists else torch.empty(0, dtype=idt, device=dev)
     n_local = rb[rank + 1] - rb[rank]
     assert send_rows.numel() == 0 or (int(send_rows.min()) >= 0 and int(send_rows.max()) < n_local)
-    return NeededRows(recv_counts, recv_offsets, send_counts, send_offsets, send_rows.contiguous(), src.contiguous())
+    dest_peer = (torch.cat(peers) if peers else torch.empty(0, dtype=torch.int32)).to(dev)
+    dest_row = (torch.cat(slots) if slots else torch.empty(0, dtype=torch.int64)).to(dev)
+    buffer_rows = max(int(table[:, 2 * world].max()), 1)
+    nd = NeededRows(recv_counts, recv_offsets, send_counts, send_rows.contiguous(), dest_peer, dest_row, buffer_rows)
+    return nd, compact
 
 
-class PipelinedGather:
-    """``gather_(weight_)scatter`` on a dst-row shard with the src-row exchange overlapped (sum / mean).
+@dataclass
+class _PeerBuffer:
+    """A symmetric-memory receive buffer as the default (CUDA) push transport holds it."""
+    handle: object                   # torch _SymmetricMemory: barrier(channel)
+    bases: torch.Tensor              # [world] int64 on the device: every peer's mapped base address of the buffer
 
-    Rows may be ``[N, F]`` (weights ``[E]`` or none) or ``[N, H, F]`` with per-head weights ``[E, H]`` (``mh_spmm``).
-    ``x_full`` is the caller's [N, ...] replica buffer whose OWN row range already holds this rank's rows (the
-    producer writes them there; ``local_rows(x_full)`` is that view).  Every call exchanges the other ranks' rows
-    into it while reducing.  ``reducer`` / ``combiner`` / ``permuter`` default to the C-ABI kernels; the gloo tests
-    inject CPU stand-ins to check the host logic."""
 
-    def __init__(self, shard: GraphShard, group=None, reducer=None, combiner=None, permuter=None,
-                 needed_only: bool = False):
-        self.shard, self.group = shard, group
+class BucketedGather:
+    """``gather_(weight_)scatter`` / ``mh_spmm`` on a dst-row shard with the src-row exchange overlapped (sum / mean).
+
+    ``transport``: ``"allgather"`` or ``"push"`` (module docstring).  Rows may be ``[n, F]`` (weights ``[E]`` or none)
+    or ``[n, H, F]`` with per-head weights ``[E, H]``.  Call with this rank's OWN rows ``x_local``.
+
+    Injectable stand-ins (the gloo tests check the host logic on CPU; defaults = the C-ABI kernels, NCCL, torch
+    symmetric memory):
+      ``reducer(x, src_ids, dst_ids, weight, edge_perm, S, out, accumulate, mean_rowptr, reduce)``
+      ``allocator(shape, dtype, device) -> (buffer, handle)``; ``pusher(x_local, nd, buffer, handle)``;
+      ``barrier(handle, channel)``."""
+
+    def __init__(self, shard: GraphShard, group=None, transport: str = "allgather", reducer=None, allocator=None,
+                 pusher=None, barrier=None):
+        assert transport in ("allgather", "push")
+        assert shard.src_index is not None
+        self.shard, self.group, self.transport = shard, group, transport
         self.world, self.rank = shard.world_size, shard.rank
-        self.buckets = bucket_by_src_owner(shard)
         self.cuda = shard.dst_index.is_cuda
-        self._reducer, self._combiner, self._permuter = reducer, combiner, permuter
-        self._plans, self._ws, self._parts, self._wperm = {}, None, None, None
-        self._rowptr = None
-        # needed_only: step k carries only the rows this rank's bucket k references (see the module docstring)
-        self.needed = build_needed_rows(shard, self.buckets, group) if needed_only else None
-        self._send_buf, self._recv_buf = None, None
+        self._reducer, self._allocator, self._pusher, self._barrier_fn = reducer, allocator, pusher, barrier
+        rb, rank = shard.row_bounds, shard.rank
+        E = shard.dst_index.numel()
+        assert E < 2 ** 31, "edge_perm is int32"
+        perm, n_local = split_local_remote(shard)
+        src = shard.src_index[perm]
+        src[:n_local] -= rb[rank]                          # bucket 0 reads the rank's own rows
+        self.needed = None
+        if transport == "push":
+            self.needed, compact = build_needed_rows(shard, src[n_local:].clone(), group)
+            src[n_local:] = compact
+        self.buckets = SrcBuckets(perm.to(torch.int32).contiguous(), [0, n_local, E], src.contiguous(),
+                                  shard.dst_index[perm].contiguous())
+        self._plans, self._ws, self._bufs, self._mean_rowptr, self._wperm = {}, {}, {}, None, None
+        self._replica = None
         self.comm_stream = torch.cuda.Stream() if self.cuda else None
-        self.events = [torch.cuda.Event() for _ in range(self.world)] if self.cuda else None
+        self.event = torch.cuda.Event() if self.cuda else None
+
+    # -- per-graph facts ------------------------------------------------------------------------------
+    def exchanged_rows(self):
+        """(rows received per call, rows a full exchange would receive)."""
+        rb = self.shard.row_bounds
+        full = rb[-1] - (rb[self.rank + 1] - rb[self.rank])
+        return (self.needed.recv_offsets[-1] if self.needed is not None else full), full
 
     def local_rows(self, x_full: torch.Tensor) -> torch.Tensor:
         rb = self.shard.row_bounds
         return x_full[rb[self.rank]:rb[self.rank + 1]]
 
-    # -- default device kernels (C ABI) ---------------------------------------------------------------
-    def _reduce_bucket(self, k, x_full, w_b, out):
+    # -- default device pieces (C ABI, NCCL, symmetric memory) ---------------------------------------------
+    def _reduce_bucket(self, k, x, weight, out, reduce, accumulate):
         b = self.buckets
         e0, e1 = b.bounds[k], b.bounds[k + 1]
         S = self.shard.num_local_rows
-        if e1 == e0 or S == 0:
-            out.zero_()
+        if S == 0:
             return
-        si, di = b.src_index[e0:e1], b.dst_index[e0:e1]
-        if self.needed is not None:
-            si = self.needed.src_index[e0:e1]      # ids into x_full = the rank's own rows (k == 0) / the compact buffer
+        if e1 == e0:
+            if not accumulate:
+                out.zero_()
+            return
+        si, di, perm = b.src_index[e0:e1], b.dst_index[e0:e1], b.perm[e0:e1]
+        mean_rowptr = None
+        if reduce == "mean":
+            if self._mean_rowptr is None:
+                deg = torch.bincount(self.shard.dst_index, minlength=S)
+                self._mean_rowptr = torch.cat([deg.new_zeros(1), deg.cumsum(0)]).contiguous()
+            mean_rowptr = self._mean_rowptr
         if self._reducer is not None:
-            out.copy_(self._reducer(x_full, si, di, w_b, S))
+            self._reducer(x, si, di, weight, perm, S, out, accumulate, mean_rowptr, reduce)
             return
         from . import abi
+        if weight is not None and weight.dim() == 2:       # [E, H] weights arrive in bucket order (_bucket_order)
+            weight, perm = weight[e0:e1], None
         if k not in self._plans:
             self._plans[k] = abi.DevicePlan(di, S)
-        if self._ws is None:
-            # one scratch buffer for all buckets: the partition (hence the scratch size) is not monotonic in E
-            W = x_full[0].numel()
-            sizes = [self.buckets.bounds[i + 1] - self.buckets.bounds[i] for i in range(len(self.buckets.bounds) - 1)]
-            need = lambda n: abi.lib().geot_b200_workspace_bytes(n, W, abi.DTYPE[x_full.dtype], 1)
-            self._ws = abi.Workspace(max(sizes, key=need), W, x_full.dtype, x_full.device)
-        H = x_full.shape[1] if x_full.dim() == 3 else 1        # [N, H, F] rows with [E, H] weights: mh_spmm
-        abi.segment_reduce(x_full, si, di, w_b, "sum", S=S, H=H, plan=self._plans[k], out=out, workspace=self._ws)
+        W = x[0].numel()
+        key = (k, W, x.dtype)                              # scratch is sized per (bucket, row width, dtype)
+        if key not in self._ws:
+            self._ws[key] = abi.Workspace(e1 - e0, W, x.dtype, x.device)
+        H = x.shape[1] if x.dim() == 3 else 1
+        abi.segment_reduce(x, si, di, weight, reduce, S=S, H=H, plan=self._plans[k], out=out, workspace=self._ws[key],
+                           accumulate=accumulate, edge_perm=perm if weight is not None else None, mean_rowptr=mean_rowptr)
 
-    def _combine(self, parts, out, reduce):
-        if self._combiner is not None:
-            out.copy_(self._combiner(parts, reduce, self.shard.dst_index, self.shard.num_local_rows))
-            return
+    def _bucket_order(self, weight):
+        """Per-head weights [E, H] in bucket order (one permutation pass per call: the kernel's edge_perm serves one
+        weight per edge only)."""
         from . import abi
-        rowptr = None
-        if reduce == "mean":
-            if self._rowptr is None:
-                self._rowptr = abi.DevicePlan(self.shard.dst_index, self.shard.num_local_rows).rowptr.clone()
-            rowptr = self._rowptr
-        abi.combine_partials(parts, out, reduce, rowptr)
+        if self._wperm is None or self._wperm.shape != weight.shape or self._wperm.dtype != weight.dtype:
+            self._wperm = torch.empty_like(weight)
+            self._perm64 = self.buckets.perm.long()
+        return abi.permute_edges(weight, self._perm64, self._wperm)
 
-    def _permute(self, w):
-        if self._permuter is not None:
-            return self._permuter(w, self.buckets.perm)
-        from . import abi
-        if self._wperm is None or self._wperm.shape != w.shape or self._wperm.dtype != w.dtype:
-            self._wperm = torch.empty_like(w)
-        return abi.permute_edges(w, self.buckets.perm, self._wperm)
-
-    # -- the op ---------------------------------------------------------------------------------------
-    def __call__(self, x_full: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum",
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        assert reduce in ("sum", "mean"), "the pipelined exchange combines partial sums: sum / mean only"
-        world, rank, rb = self.world, self.rank, self.shard.row_bounds
-        S = self.shard.num_local_rows
-        tail = list(x_full.shape[1:])
-        if out is None:
-            out = x_full.new_empty([S] + tail)
-        if self._parts is None or list(self._parts.shape[2:]) != tail or self._parts.dtype != x_full.dtype:
-            self._parts = x_full.new_empty([world, S] + tail)
-        parts = self._parts
-        nd = self.needed
-        n_local = rb[rank + 1] - rb[rank]
-        # needed_only accepts the rank's own rows [n_local, ...] as well as the [N, ...] buffer (only its own range is read)
-        x_mine = x_full if (nd is not None and x_full.shape[0] == n_local) else self.local_rows(x_full)
-        if nd is not None:
-            n_send, n_recv = nd.send_offsets[-1], nd.recv_offsets[-1]
-            if self._send_buf is None or list(self._send_buf.shape[1:]) != tail or self._send_buf.dtype != x_full.dtype:
-                self._send_buf = x_full.new_empty([max(n_send, 1)] + tail)
-                self._recv_buf = x_full.new_empty([max(n_recv, 1)] + tail)
-
-        # exchange: world-1 staggered send/recv steps on the side stream
-        if self.cuda:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())   # my rows are final; x_full's old rows were consumed
-        if nd is not None and n_send:
-            if self.cuda:
-                with torch.cuda.stream(self.comm_stream):
-                    self._pack(x_mine, nd.send_rows, self._send_buf)
-            else:
-                self._pack(x_mine, nd.send_rows, self._send_buf)
-        for k in range(1, world):
-            to, frm = (rank - k) % world, (rank + k) % world
-            ops = []
-            if nd is None:
-                if x_mine.shape[0]:
-                    ops.append(dist.P2POp(dist.isend, x_mine, to, self.group))
-                if rb[frm + 1] > rb[frm]:
-                    ops.append(dist.P2POp(dist.irecv, x_full[rb[frm]:rb[frm + 1]], frm, self.group))
-                # (a rank with an empty row range neither sends nor is received from: both sides skip consistently)
-            else:
-                if nd.send_counts[to]:
-                    ops.append(dist.P2POp(dist.isend, self._send_buf[nd.send_offsets[k - 1]:nd.send_offsets[k]], to, self.group))
-                if nd.recv_counts[frm]:
-                    ops.append(dist.P2POp(dist.irecv, self._recv_buf[nd.recv_offsets[k - 1]:nd.recv_offsets[k]], frm, self.group))
-                # (send_counts[to] here == recv_counts[me] on rank `to`: both sides skip an empty step consistently)
-            if self.cuda:
-                with torch.cuda.stream(self.comm_stream):
-                    if ops:
-                        for r in dist.batch_isend_irecv(ops):
-                            r.wait()
-                    self.events[k].record(self.comm_stream)
-            elif ops:
-                for r in dist.batch_isend_irecv(ops):
-                    r.wait()
-
-        # reduction: own bucket first, bucket k once step k has landed
-        w_all = self._permute(weight) if weight is not None else None
-        b = self.buckets.bounds
-        for k in range(world):
-            if k > 0 and self.cuda:
-                torch.cuda.current_stream().wait_event(self.events[k])
-            w_b = w_all[b[k]:b[k + 1]] if w_all is not None else None
-            x_k = x_full if nd is None else (x_mine if k == 0 else self._recv_buf)
-            self._reduce_bucket(k, x_k, w_b, parts[k])
-        self._combine(parts, out, reduce)
-        return out
-
-    def aggregate(self, x_local: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum") -> torch.Tensor:
-        """The op on this rank's OWN rows ``x_local`` (what a layer produces): the full-exchange form keeps its
-        ``[N, ...]`` replica buffer here (one per row shape / dtype) and copies the rows into their range; the
-        needed-rows form reads them in place.  Returns a new ``[n_local_rows, ...]`` tensor."""
-        if self.needed is not None:
-            return self(x_local, weight, reduce)
-        tail = list(x_local.shape[1:])
-        buf = getattr(self, "_replica", None)
-        if buf is None or list(buf.shape[1:]) != tail or buf.dtype != x_local.dtype or buf.device != x_local.device:
-            buf = self._replica = x_local.new_empty([self.shard.row_bounds[-1]] + tail)
-        self.local_rows(buf).copy_(x_local)
-        return self(buf, weight, reduce)
-
-    def _pack(self, x_mine, rows, out):
-        """out[i] = x_mine[rows[i]]: the rows the peers asked for, grouped by peer in step order."""
-        if self._permuter is not None:
-            out[: rows.numel()].copy_(self._permuter(x_mine, rows))
-            return
-        from . import abi
-        abi.permute_edges(x_mine, rows, out)
-
-    def exchanged_rows(self):
-        """(rows received per call, rows a full exchange would receive) -- the saving of needed_only."""
-        rb = self.shard.row_bounds
-        full = rb[-1] - (rb[self.rank + 1] - rb[self.rank])
-        return (self.needed.recv_offsets[-1] if self.needed is not None else full), full
-
-
-@dataclass
-class _PeerBuffer:
-    """A symmetric-memory receive buffer as the default (CUDA) path of PeerPushGather holds it."""
-    handle: object                   # torch _SymmetricMemory: barrier(channel)
-    bases: torch.Tensor              # [world] int64 on the device: every peer's mapped base address of the buffer
-
-
-class PeerPushGather(PipelinedGather):
-    """``gather_(weight_)scatter`` on a dst-row shard with the needed src rows PUSHED over peer memory (sum / mean).
-
-    Per graph: the request lists of the needed-rows exchange (``build_needed_rows``), the slot of every requested row
-    in its requester's receive buffer (``dest_peer`` / ``dest_row``), and the rank's edges split stably into two
-    dst-sorted buckets -- src row local / src row remote -- with src ids that point into ``x_local`` / the receive
-    buffer.  Per call (side stream): barrier (every peer has finished reading its buffer), one push kernel, barrier
-    (every peer's rows have landed here); (main stream): local bucket, wait, remote bucket, combine.
-
-    ``allocator(shape, dtype, device) -> (buffer, handle)``, ``pusher(x_mine, rows, dest_peer, dest_row, buffer, handle)``
-    and ``barrier(handle, channel)`` default to torch symmetric memory + the C-ABI kernel; the gloo tests inject CPU
-    stand-ins to check the host logic (slots, buckets, ordering)."""
-
-    def __init__(self, shard: GraphShard, group=None, reducer=None, combiner=None, permuter=None, allocator=None,
-                 pusher=None, barrier=None):
-        self.shard, self.group = shard, group
-        self.world, self.rank = world, rank = shard.world_size, shard.rank
-        self.cuda = shard.dst_index.is_cuda
-        self._reducer, self._combiner, self._permuter = reducer, combiner, permuter
-        self._allocator, self._pusher, self._barrier_fn = allocator, pusher, barrier
-        self._plans, self._ws, self._parts, self._wperm = {}, None, None, None
-        self._rowptr = None
-        self.needed = None                                  # (the base class's NCCL needed-rows state: not used here)
-        self._bufs = {}
-        dev = shard.dst_index.device
-        per_owner = bucket_by_src_owner(shard)
-        self.requests = nd = build_needed_rows(shard, per_owner, group)
-        E = shard.dst_index.numel()
-        # src ids in shard edge order, then the stable two-way split (local first): both halves stay dst-sorted
-        compact = torch.empty_like(nd.src_index)
-        compact[per_owner.perm] = nd.src_index
-        remote = torch.ones(E, dtype=torch.int8, device=dev)
-        remote[per_owner.perm[: per_owner.bounds[1]]] = 0
-        perm2 = torch.argsort(remote, stable=True)
-        self.buckets = SrcBuckets(perm2, [0, per_owner.bounds[1], E], compact[perm2].contiguous(),
-                                  shard.dst_index[perm2].contiguous())
-        # slots: my send segment k (for rank - k) lands at that rank's receive offset of ITS step k (owner = me)
-        mine = torch.tensor(nd.recv_offsets, dtype=torch.int64, device=dev)
-        table = torch.empty(world * (world + 1), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(table, mine, group=group)
-        table = table.view(world, world + 1).cpu()
-        peers, slots = [], []
-        for k in range(1, world):
-            to = (rank - k) % world
-            n = nd.send_counts[to]
-            peers.append(torch.full((n,), to, dtype=torch.int32))
-            slots.append(int(table[to][k - 1]) + torch.arange(n, dtype=torch.int64))
-        self.dest_peer = (torch.cat(peers) if peers else torch.empty(0, dtype=torch.int32)).to(dev)
-        self.dest_row = (torch.cat(slots) if slots else torch.empty(0, dtype=torch.int64)).to(dev)
-        self.buffer_rows = max(int(table[:, -1].max()), 1)   # same size on every rank (symmetric allocation)
-        self.comm_stream = torch.cuda.Stream() if self.cuda else None
-        self.event = torch.cuda.Event() if self.cuda else None
-
-    # -- defaults: torch symmetric memory + the C-ABI push kernel ---------------------------------------------
     def _buffer(self, tail, dtype, device):
+        """The buffer bucket 1 gathers from: the [N, ...] replica (allgather) or the symmetric receive buffer (push)."""
         key = (tuple(tail), dtype)
-        if key not in self._bufs:
-            shape = [self.buffer_rows] + list(tail)
+        if key in self._bufs:
+            return self._bufs[key]
+        if self.transport == "allgather":
+            self._bufs[key] = (torch.empty([self.shard.row_bounds[-1]] + list(tail), dtype=dtype, device=device), None)
+        else:
+            shape = [self.needed.buffer_rows] + list(tail)
             if self._allocator is not None:
                 self._bufs[key] = self._allocator(shape, dtype, device)
             else:
@@ -498,20 +369,22 @@ class PeerPushGather(PipelinedGather):
                     pass
                 buf = symm.empty(shape, dtype=dtype, device=device)
                 hdl = symm.rendezvous(buf, pg)
-                # the peers' mapped base addresses as a device array (what geot_b200_push_rows indexes by dest_peer)
                 bases = torch.tensor([int(a) for a in hdl.buffer_ptrs], dtype=torch.int64, device=device)
                 self._bufs[key] = (buf, _PeerBuffer(hdl, bases))
         return self._bufs[key]
 
-    def _push(self, x_mine, buf, hdl):
-        nd = self.requests
-        if self._pusher is not None:       # (a stand-in also plays the receiving side, so it runs even with nothing to send)
-            self._pusher(x_mine, nd.send_rows, self.dest_peer, self.dest_row, buf, hdl)
+    def _exchange(self, x_local, buf, hdl):
+        if self.transport == "allgather":
+            all_gather_rows(x_local, self.shard.row_bounds, self.group, out=buf)
             return
-        if nd.send_rows.numel() == 0:
-            return
-        from . import abi
-        abi.push_rows(x_mine, nd.send_rows, self.dest_peer, self.dest_row, hdl.bases.data_ptr())
+        nd = self.needed
+        self._barrier(hdl, 0)              # every peer is done reading its receive buffer (its previous call)
+        if self._pusher is not None:       # (a stand-in also plays the receiving side: runs even with nothing to send)
+            self._pusher(x_local, nd, buf, hdl)
+        elif nd.send_rows.numel():
+            from . import abi
+            abi.push_rows(x_local, nd.send_rows, nd.dest_peer, nd.dest_row, hdl.bases.data_ptr())
+        self._barrier(hdl, 1)              # every peer's rows are in my buffer
 
     def _barrier(self, hdl, channel):
         if self._barrier_fn is not None:
@@ -519,95 +392,32 @@ class PeerPushGather(PipelinedGather):
         else:
             hdl.handle.barrier(channel=channel)
 
-    def aggregate(self, x_local, weight=None, reduce="sum"):
-        return self(x_local, weight, reduce)
-
-    def exchanged_rows(self):
-        rb = self.shard.row_bounds
-        return self.requests.recv_offsets[-1], rb[-1] - (rb[self.rank + 1] - rb[self.rank])
-
-    def __call__(self, x: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum",
+    # -- the op -------------------------------------------------------------------------------------------
+    def __call__(self, x_local: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum",
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        assert reduce in ("sum", "mean"), "bucket partials are combined by addition: sum / mean only"
-        rb, rank = self.shard.row_bounds, self.rank
+        assert reduce in ("sum", "mean"), "bucket partials add up: sum / mean only (max / min: sharded_gather_scatter)"
         S = self.shard.num_local_rows
-        x_mine = x if x.shape[0] == S else self.local_rows(x)       # own rows, or the [N, ...] buffer holding them
-        x_mine = x_mine.contiguous()
-        tail = list(x_mine.shape[1:])
+        assert x_local.shape[0] == S, "pass this rank's own rows"
+        x_local = x_local.contiguous()
+        tail = list(x_local.shape[1:])
         if out is None:
-            out = x_mine.new_empty([S] + tail)
-        if self._parts is None or list(self._parts.shape[2:]) != tail or self._parts.dtype != x_mine.dtype:
-            self._parts = x_mine.new_empty([2, S] + tail)
-        parts = self._parts
-        buf, hdl = self._buffer(tail, x_mine.dtype, x_mine.device)
-
-        def exchange():
-            self._barrier(hdl, 0)          # every peer is done reading its receive buffer (its previous call)
-            self._push(x_mine, buf, hdl)   # my rows into their slots on the peers
-            self._barrier(hdl, 1)          # every peer's rows are in my buffer
-
+            out = x_local.new_empty([S] + tail)
+        buf, hdl = self._buffer(tail, x_local.dtype, x_local.device)
         if self.cuda:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            self.comm_stream.wait_stream(torch.cuda.current_stream())   # x_local is final; buf's old rows were consumed
             with torch.cuda.stream(self.comm_stream):
-                exchange()
+                self._exchange(x_local, buf, hdl)
                 self.event.record(self.comm_stream)
         else:
-            exchange()
-
-        w_all = self._permute(weight) if weight is not None else None
-        b = self.buckets.bounds
-        self._reduce_bucket(0, x_mine, w_all[b[0]:b[1]] if w_all is not None else None, parts[0])
+            self._exchange(x_local, buf, hdl)
+        if weight is not None and weight.dim() == 2 and self._reducer is None:
+            weight = self._bucket_order(weight)
+        self._reduce_bucket(0, x_local, weight, out, reduce, accumulate=False)
         if self.cuda:
             torch.cuda.current_stream().wait_event(self.event)
-        self._reduce_bucket(1, buf, w_all[b[1]:b[2]] if w_all is not None else None, parts[1])
-        self._combine(parts, out, reduce)
+        self._reduce_bucket(1, buf, weight, out, reduce, accumulate=True)
         return out
 
-
-class SrcBlockedGather(PipelinedGather):
-    """Single-GPU experiment: temporal blocking of the src matrix for L2.  The edges are split stably into ``blocks``
-    buckets by src row range (each still dst-sorted) and reduced one bucket after the other, so that at any time the
-    gathers touch ``1/blocks`` of the src matrix; the bucket partials are combined in bucket order.  Pays only when
-    the saved DRAM re-reads exceed the partial-sum traffic (``2*blocks + 1`` passes over the output): high-degree
-    graphs whose src matrix is a small multiple of the L2 (Reddit-shape: 119 MB src, degree 492), not products-like
-    ones.  Same kernels, same plans per bucket, no communication."""
-
-    def __init__(self, src_index: torch.Tensor, dst_index: torch.Tensor, num_dst_rows: int, num_src_rows: int,
-                 blocks: int, reducer=None, combiner=None, permuter=None):
-        E = dst_index.numel()
-        self.shard = GraphShard(0, 1, [0, num_dst_rows], [0, E], src_index, dst_index, None)
-        self.group, self.world, self.rank = None, 1, 0
-        self.cuda = dst_index.is_cuda
-        self._reducer, self._combiner, self._permuter = reducer, combiner, permuter
-        self._plans, self._ws, self._parts, self._wperm = {}, None, None, None
-        self._rowptr, self.needed = None, None
-        self.blocks = blocks
-        rows_per_block = (num_src_rows + blocks - 1) // blocks
-        key = torch.div(src_index, rows_per_block, rounding_mode="floor")
-        perm = torch.argsort(key, stable=True)
-        counts = torch.bincount(key, minlength=blocks).tolist()
-        bounds = [0]
-        for c in counts:
-            bounds.append(bounds[-1] + int(c))
-        self.buckets = SrcBuckets(perm, bounds, src_index[perm].contiguous(), dst_index[perm].contiguous())
-
-    def permute_weight(self, weight: torch.Tensor) -> torch.Tensor:
-        """Per-edge weights in bucket order (a copy): pass it with ``permuted=True`` when the weights are static."""
-        return self._permute(weight).clone()
-
-    def __call__(self, x: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum",
-                 out: Optional[torch.Tensor] = None, permuted: bool = False) -> torch.Tensor:
-        assert reduce in ("sum", "mean"), "bucket partials are combined by addition: sum / mean only"
-        S = self.shard.num_local_rows
-        tail = list(x.shape[1:])
-        if out is None:
-            out = x.new_empty([S] + tail)
-        if self._parts is None or list(self._parts.shape[2:]) != tail or self._parts.dtype != x.dtype:
-            self._parts = x.new_empty([self.blocks, S] + tail)
-        w_all = None if weight is None else (weight if permuted else self._permute(weight))
-        b = self.buckets.bounds
-        for k in range(self.blocks):
-            self._reduce_bucket(k, x, w_all[b[k]:b[k + 1]] if w_all is not None else None, self._parts[k])
-        self._combine(self._parts, out, reduce)
-        return out
-
+    def aggregate(self, x_local: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum") -> torch.Tensor:
+        """The op on this rank's own rows (what a layer produces); returns a new ``[n_local_rows, ...]`` tensor."""
+        return self(x_local, weight, reduce)

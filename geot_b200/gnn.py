@@ -16,7 +16,7 @@ PyG / torch_sparse are not part of this build, so the same math is restated on p
 The dense ``lin`` layers are cuBLAS GEMMs through ``torch.nn.Linear`` (library code, not part of the hot
 path).  ``forward_sharded`` runs the same stack with the node rows sharded over the GPUs of one box
 (``geot_b200.dist``): the GEMM is row-local with replicated weights, the aggregation exchanges the src
-rows once per layer (one all-gather, or the pipelined / needed-rows exchange of ``PipelinedGather``).
+rows once per layer (one all-gather, or the overlapped two-bucket exchange of ``dist.BucketedGather``).
 """
 from typing import List, Optional
 
@@ -128,10 +128,10 @@ def forward_sharded(model: _Stack, x_local: torch.Tensor, shard, group=None, gat
     the exchange of the src rows, aggregation into the local dst rows.  ``shard.weight`` carries the
     (globally normalised) GCN weights for a GCN stack and is ``None`` for GraphSAGE.
 
-    ``gather``: a ``geot_b200.dist.PipelinedGather`` built once for ``shard`` -- the exchange is then overlapped
-    with the reduction (full or needed-rows form, whichever the object was built with) and its per-graph state
-    (buckets, plans, request lists) is shared by all layers.  ``None``: one all-gather per layer.  Forward only
-    (the pipelined exchange is not differentiable)."""
+    ``gather``: a ``geot_b200.dist.BucketedGather`` built once for ``shard`` -- the exchange is then overlapped
+    with the reduction (all-gather or needed-rows push transport, whichever the object was built with) and its
+    per-graph state (buckets, plans, request lists) is shared by all layers.  ``None``: one all-gather per layer.
+    Forward only (the overlapped exchange is not differentiable)."""
     from . import dist as gdist
 
     def aggregate(h):

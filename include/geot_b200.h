@@ -35,7 +35,7 @@ extern "C" {
 typedef struct CUstream_st *cudaStream_t;
 #endif
 
-#define GEOT_B200_VERSION 100 /* 0.1.0 */
+#define GEOT_B200_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define GEOT_API __attribute__((visibility("default")))
@@ -84,6 +84,7 @@ typedef struct geot_plan {
   const int64_t *rowptr;  /* device, S+1 entries: CSR row pointer == geot::coo_to_csr
                              (geot/match_replace/format_transform.py:5-18); segment r covers edges
                              [rowptr[r], rowptr[r+1]) */
+  int64_t max_row;        /* largest value in dst_index (== dst_index[E-1] when sorted) */
 } geot_plan_t;
 
 /* Highest index: reads dst_index[E-1] (sorted input) -- one 8-byte D2H copy, synchronises `stream`. */
@@ -123,6 +124,30 @@ GEOT_API int geot_b200_segment_reduce(const void *src, const int64_t *src_index,
                              int64_t F, int dtype, int reduce, int weight_layout, int sorted,
                              const geot_plan_t *plan, void *workspace, size_t workspace_bytes,
                              cudaStream_t stream);
+
+/* Options of geot_b200_segment_reduce_ex (zero-initialise, set struct_size = sizeof(geot_reduce_opts_t)).
+ * They serve reductions that run as several passes over disjoint edge buckets of ONE graph -- the multi-GPU
+ * two-bucket exchange (edges whose src row is local are reduced while the remote rows are in flight, the rest
+ * afterwards: geot_b200/dist.py) -- without a combine pass and without re-ordering the caller's weights:
+ *   accumulate   != 0: dst[r] += result for the rows this pass touches, other rows untouched (sum, or mean with
+ *                mean_rowptr); the first pass runs with accumulate == 0 and writes every row of dst.
+ *   edge_perm    [E] int32, device: the weight of edge e of THIS pass is weight[edge_perm[e]] (the bucket keeps the
+ *                caller's weight order).  GEOT_W_EDGE weights, sorted input, sum / mean only.
+ *   mean_rowptr  [S+1] int64, device: reduce == GEOT_MEAN divides by mean_rowptr[r+1] - mean_rowptr[r] (the row's
+ *                degree in the complete edge list) instead of by this pass's own count, so partial means add up. */
+typedef struct geot_reduce_opts {
+  size_t struct_size;
+  int32_t accumulate;
+  int32_t reserved;
+  const int32_t *edge_perm;
+  const int64_t *mean_rowptr;
+} geot_reduce_opts_t;
+
+GEOT_API int geot_b200_segment_reduce_ex(const void *src, const int64_t *src_index, const int64_t *dst_index,
+                                const void *weight, void *dst, int64_t E, int64_t S, int64_t H,
+                                int64_t F, int dtype, int reduce, int weight_layout, int sorted,
+                                const geot_plan_t *plan, void *workspace, size_t workspace_bytes,
+                                cudaStream_t stream, const geot_reduce_opts_t *opts);
 
 /* Replaces index_scatter_cuda (header_cuda.h:4-6; csrc/cuda/index_scatter_cuda.cu:86-105), dim = 0:
  * src viewed as [E, F] (wrapper/index_scatter_base.h:15-17).  sorted == 0 takes the atomic kernel
@@ -168,16 +193,9 @@ GEOT_API int geot_b200_csr_to_coo(const void *rowptr, int rowptr_bits, int64_t S
 
 /* ---- multi-GPU helpers (dst-row shards; new -- the reference has no distributed code) ---------- */
 
-/* dst[r, :] = parts[0][r, :] + parts[1][r, :] + ... (in this order; fp32 / fp64 accumulation), divided by the
- * degree rowptr[r+1] - rowptr[r] when reduce == GEOT_MEAN.  parts: n_parts matrices [S, W] of `dtype`,
- * part_stride elements apart.  Finishes a gather op whose edges were reduced in buckets (one per src-row owner,
- * each while the next owner's rows were still in flight over NVLink): geot_b200/dist.py. */
-GEOT_API int geot_b200_combine_partials(const void *parts, int n_parts, int64_t part_stride, void *dst, int64_t S,
-                               int64_t W, int dtype, int reduce, const int64_t *rowptr, cudaStream_t stream);
-
-/* out[e] = in[perm[e]] for records of bytes_per_edge bytes (even): carries per-edge weights into bucket order, and
- * packs the feature rows a peer asked for (perm = the requested local row ids, bytes_per_edge = the row size; moved
- * as 16-byte vectors when size and pointers allow). */
+/* out[e] = in[perm[e]] for records of bytes_per_edge bytes (even): carries per-head edge weights [E, H] into bucket
+ * order (one weight per edge needs no pass: geot_reduce_opts_t.edge_perm), or packs feature rows (perm = row ids,
+ * bytes_per_edge = the row size; moved as 16-byte vectors when size and pointers allow). */
 GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *out, int64_t E, int64_t bytes_per_edge,
                             cudaStream_t stream);
 
@@ -185,9 +203,9 @@ GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *
  *     peer_bases[dest_peer[e]][dest_row[e], :] = x[rows[e], :]          e = 0 .. n-1,  rows of row_bytes bytes
  * peer_bases: DEVICE array of base pointers, one per GPU of the group, each the receive buffer of that GPU mapped
  * into this process (torch symmetric memory: _SymmetricMemory.buffer_ptrs_dev; cudaIpc / cuMem mappings work the
- * same); peers_aligned16 != 0 promises those bases are 16-byte aligned.  row_bytes must be a multiple of 4.  The
+ * same); peers_aligned16 != 0 promises those bases are 16-byte aligned.  row_bytes must be even.  The
  * stores are complete when the kernel is; the caller orders them against the consumers with a cross-GPU barrier on
- * `stream` (geot_b200/dist.py PeerPushGather).  rows / dest_peer / dest_row are built once per graph. */
+ * `stream` (geot_b200/dist.py BucketedGather, transport "push").  rows / dest_peer / dest_row are built once per graph. */
 GEOT_API int geot_b200_push_rows(const void *x, const int64_t *rows, const int32_t *dest_peer, const int64_t *dest_row,
                         void *const *peer_bases, int64_t n, int64_t row_bytes, int peers_aligned16,
                         cudaStream_t stream);
@@ -222,11 +240,30 @@ GEOT_API int geot_b200_segment_reduce_host(const void *src, int64_t N_src, const
                                   int weight_layout);
 GEOT_API int geot_b200_host_arena_release(void);
 
-/* Compact transport of the host-buffer entry (environment GEOT_B200_HOST_COMPACT, bit mask, default 0 = off):
- *   1: each slice sends its CSR row pointer (rows + 1 values, computed by the host threads below) instead of its
- *      dst_index (one value per edge); the device expands it (the inverse of geot::coo_to_csr);
- *   2: src_index travels as int32 (narrowed by the host threads, widened on the device; N_src < 2^31).
- * Results are identical; the bytes over the link drop (Reddit-shape gather_weight_scatter: 2.41 -> 1.49 -> 1.04 GB).
+/* Resident host graph: the index arrays of a graph are uploaded ONCE; every reduce call then moves only what
+ * changes from call to call (src rows and edge weights in, dst rows out).  A GNN's graph is static across layers and
+ * epochs, so this is the host-buffer call a training / serving loop makes after the first step.
+ *   create   src_index [E] (or NULL: src row = edge id, index_scatter) and dst_index [E] (sorted) in HOST memory;
+ *            S dst rows, N_src src rows.  Synchronous; the handle belongs to the current device.
+ *   reduce   src [N_src, H*F] (or [E, H*F] when created without src_index), weight per weight_layout (or NULL), dst
+ *            [S, H*F], all in HOST memory (pinned memory makes the copies asynchronous).  The edge list is processed
+ *            in slices cut at segment boundaries: the weights (and edge-aligned src rows) of slice k+1 travel while
+ *            slice k is reduced and the finished dst rows of slice k-1 go home.  Returns when dst is complete.
+ *   last_transfer  bytes the last reduce moved over the link per direction, and the bytes made resident by create.
+ * One call at a time per handle. */
+typedef struct geot_host_graph geot_host_graph_t;
+GEOT_API int geot_b200_host_graph_create(const int64_t *src_index, const int64_t *dst_index, int64_t E, int64_t S,
+                                int64_t N_src, geot_host_graph_t **graph);
+GEOT_API int geot_b200_host_graph_reduce(geot_host_graph_t *graph, const void *src, const void *weight, void *dst,
+                                int64_t H, int64_t F, int dtype, int reduce, int weight_layout);
+GEOT_API int geot_b200_host_graph_last_transfer(const geot_host_graph_t *graph, unsigned long long *h2d_bytes,
+                                       unsigned long long *d2h_bytes, unsigned long long *resident_bytes);
+GEOT_API int geot_b200_host_graph_destroy(geot_host_graph_t *graph);
+
+/* Row-pointer transport of the host-buffer entry (default; environment GEOT_B200_HOST_COMPACT=0 turns it off): each
+ * slice sends its CSR row pointer (rows + 1 values, computed by the host threads below) instead of its dst_index (one
+ * value per edge); the device expands it (the inverse of geot::coo_to_csr).  Results are identical; the bytes over
+ * the link drop (Reddit-shape gather_weight_scatter: 2.41 -> 1.49 GB, 44.5 -> 28.1 ms).
  * GEOT_B200_HOST_THREADS bounds the host threads (default: hardware concurrency, at most 32).
  * geot_b200_host_last_transfer reports the bytes the last host call really moved in each direction. */
 GEOT_API int geot_b200_host_last_transfer(unsigned long long *h2d_bytes, unsigned long long *d2h_bytes);

@@ -76,6 +76,11 @@ def rowptr(index: torch.Tensor, S: int) -> torch.Tensor:
     return out
 
 
+def set_threads(n: int = 0) -> int:
+    """Sets (n > 0) and returns the OpenMP thread count of the threaded baseline variant."""
+    return int(lib().geot_oracle_set_threads(ctypes.c_int(n)))
+
+
 def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H=1,
                    weight_transposed=False, acc64=False, threads=False):
     """dst[dst_index[e]] (op)= weight[e,h] * src[src_index[e]]   on CPU tensors.

@@ -183,6 +183,18 @@ int geot_oracle_reduce_f32_mt(const float *src, const int64_t *src_index, const 
   return nthreads;
 }
 
+/* Threads of the timed CPU baseline.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently time a
+ * single-threaded baseline: the bench sets the count explicitly and reports what the runtime really uses. */
+int geot_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 /* ---- SDDMM on a COO edge list ---------------------------------------------------------------- */
 
 /* out[e] = < mat1[row[e], :], mat2[col[e], :] >.  Follows the reference kernel's definition

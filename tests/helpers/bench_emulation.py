@@ -37,6 +37,7 @@ def install(rank=0, world=1):
     torch.cuda.synchronize = lambda *a: None
     torch.cuda.empty_cache = lambda: None
     torch.cuda.Event = FakeEvent
+    torch.cuda.current_stream = lambda *a: types.SimpleNamespace(synchronize=lambda: None, cuda_stream=0)
     torch.Tensor.pin_memory = lambda self: self
     orig_device = torch.device
     torch.device = lambda *a, **k: orig_device("cpu") if (a and a[0] == "cuda") else orig_device(*a, **k)
@@ -56,16 +57,22 @@ def install(rank=0, world=1):
             self.nbytes = 0
 
     def segment_reduce(src, si, di, w, reduce="sum", *, S=None, H=1, weight_layout=None, sorted=True, plan=None, out=None,
-                       workspace=None):
-        r = oracle.segment_reduce(src.float(), si, di, None if w is None else w.float(), reduce, S=S, H=H).to(src.dtype)
+                       workspace=None, accumulate=False, edge_perm=None, mean_rowptr=None):
+        if w is not None and edge_perm is not None:
+            w = w[edge_perm.long()]
+        red = "sum" if mean_rowptr is not None else reduce
+        r = oracle.segment_reduce(src.float(), si, di, None if w is None else w.float(), red, S=S, H=H)
+        if mean_rowptr is not None and reduce == "mean":
+            deg = (mean_rowptr[1:] - mean_rowptr[:-1]).clamp_min(1).float()
+            r = r / deg.view([-1] + [1] * (r.dim() - 1))
+        r = r.to(src.dtype)
         if out is not None:
-            out.copy_(r)
+            if accumulate:
+                out += r
+            else:
+                out.copy_(r)
             return out
         return r
-
-    def combine(parts, out, reduce="sum", rowptr=None):
-        out.copy_(parts.float().sum(0).to(parts.dtype))
-        return out
 
     def permute(x, perm, out=None):
         r = x[perm]
@@ -74,15 +81,28 @@ def install(rank=0, world=1):
             return out
         return r
 
+    class HostGraph:
+        def __init__(self, si, di, S, N_src):
+            self.si, self.di, self.S = si, di, S
+
+        def reduce(self, src, weight=None, reduce="sum", *, H=1, weight_layout=None, out=None):
+            return segment_reduce(src, self.si, self.di, weight, reduce, S=self.S, H=H, out=out)
+
+        def last_transfer(self):
+            return (700, 10, 5000)
+
+        def close(self):
+            pass
+
     calls = {"n": 0}
-    abi.DevicePlan, abi.Workspace, abi.segment_reduce = DevicePlan, Workspace, segment_reduce
+    abi.DevicePlan, abi.Workspace, abi.segment_reduce, abi.HostGraph = DevicePlan, Workspace, segment_reduce, HostGraph
     abi.segment_reduce_host = (lambda src, si, di, w, reduce="sum", *, S, H=1, weight_layout=None, out=None:
                                segment_reduce(src, si, di, w, reduce, S=S, H=H, out=out))
-    abi.combine_partials, abi.permute_edges = combine, permute
+    abi.permute_edges = permute
     abi.profile_enable = lambda n: calls.__setitem__("n", n)
     abi.profile_read = lambda cap=4096: [0.05] * min(cap, max(calls["n"], 1))
     abi.host_last_transfer = lambda: (1000, 10)
-    abi.lib = lambda: types.SimpleNamespace(geot_b200_workspace_bytes=lambda *a: 256)
+    abi.lib = lambda: types.SimpleNamespace(geot_b200_workspace_bytes=lambda *a: 256, geot_b200_host_arena_release=lambda: 0)
 
 
 def run_own(workload, world=1, steps=2, warmup=3):

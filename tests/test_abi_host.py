@@ -33,11 +33,11 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_arch_status_strings():
     L = abi.lib()
-    assert L.geot_b200_version() == 100
+    assert L.geot_b200_version() == 200
     assert L.geot_b200_arch() == 100
     assert L.geot_b200_status_string(0) == b"ok"
     assert b"invalid" in L.geot_b200_status_string(1)
-    assert torch.ops.geot.abi_version() == 100
+    assert torch.ops.geot.abi_version() == 200
 
 
 def test_library_is_sm100a_only():

@@ -68,86 +68,64 @@ def _worker(rank, world, port, q, hub=False):
             local = torch.zeros(shard.num_local_rows, F)
         full = oracle.gather_weight_scatter(src_index, dst, weight, x, reduce)
         assert torch.equal(local, full[rb[rank]:rb[rank + 1]]), reduce
-    # exchange overlapped with the reduction: staggered send/recv steps + per-owner buckets + combine.  CPU stand-ins
-    # (oracle as the checker) for the three device kernels; the host logic under test is the bucketing, the step
-    # schedule and the bucket order.
-    def reducer(xf, si, di, w, S):
-        return oracle.segment_reduce(xf, si, di, w, "sum", S=S, H=(xf.shape[1] if xf.dim() == 3 else 1))
-
-    def combiner(parts, reduce, dst_local, S):
-        tot = parts.sum(0)
+    # exchange overlapped with the reduction (BucketedGather): stable local / remote split, first pass writes every row,
+    # second pass accumulates, weights read through edge_perm, mean by the full degree.  CPU stand-in for the device
+    # kernel (the oracle as the checker) honouring the same contract as geot_b200_segment_reduce_ex; the host logic
+    # under test is the bucketing, the src ids per transport, the slot arithmetic of the push and the pass order.
+    def reducer(xf, si, di, w, perm, S, out, accumulate, mean_rowptr, reduce):
+        ww = None
+        if w is not None:
+            ww = w[perm.long()] if w.dim() == 1 else w[perm.long()]
+        part = oracle.segment_reduce(xf, si, di, ww, "sum", S=S, H=(xf.shape[1] if xf.dim() == 3 else 1))
         if reduce == "mean":
-            deg = torch.bincount(dst_local, minlength=S).clamp_min(1).to(tot.dtype)
-            tot = tot / deg.view([-1] + [1] * (tot.dim() - 1))
-        return tot
+            deg = (mean_rowptr[1:] - mean_rowptr[:-1]).clamp_min(1).to(part.dtype)
+            part = part / deg.view([-1] + [1] * (part.dim() - 1))
+        if accumulate:
+            out += part
+        else:
+            out.copy_(part)
 
-    pg = gdist.PipelinedGather(shard, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm])
-    b = pg.buckets
-    assert b.bounds[0] == 0 and b.bounds[-1] == shard.num_local_edges
-    for k in range(world):
-        owner = (rank + k) % world
-        s_k = b.src_index[b.bounds[k]:b.bounds[k + 1]]
-        assert bool(((s_k >= rb[owner]) & (s_k < rb[owner + 1])).all())
-        d_k = b.dst_index[b.bounds[k]:b.bounds[k + 1]]
-        assert bool((d_k[1:] >= d_k[:-1]).all())                       # stable regrouping keeps dst order
+    def check_buckets(bg):
+        b = bg.buckets
+        assert b.bounds[0] == 0 and b.bounds[2] == shard.num_local_edges and b.perm.dtype == torch.int32
+        glob = shard.src_index[b.perm.long()]
+        loc = (glob >= rb[rank]) & (glob < rb[rank + 1])
+        assert bool(loc[: b.bounds[1]].all()) and not bool(loc[b.bounds[1]:].any())
+        assert torch.equal(b.src_index[: b.bounds[1]], glob[: b.bounds[1]] - rb[rank])
+        for k in range(2):
+            d_k = b.dst_index[b.bounds[k]:b.bounds[k + 1]]
+            assert bool((d_k[1:] >= d_k[:-1]).all())                   # stable split keeps dst order
+
+    def expect(reduce, weighted):
+        full = (oracle.gather_weight_scatter(src_index, dst, weight, x, reduce) if weighted
+                else oracle.gather_scatter(src_index, dst, x, reduce))
+        return full[rb[rank]:rb[rank + 1]]
+
+    bg = gdist.BucketedGather(shard, transport="allgather", reducer=reducer)
+    check_buckets(bg)
+    assert torch.equal(bg.buckets.src_index[bg.buckets.bounds[1]:], shard.src_index[bg.buckets.perm.long()][bg.buckets.bounds[1]:])
     for reduce in ["sum", "mean"]:
-        for wt in (None, weight):
-            x_buf = torch.full((N, F), float("nan"))
-            pg.local_rows(x_buf).copy_(x_local)
-            shard_w = shard.weight if wt is not None else None
-            got = pg(x_buf, shard_w, reduce)
-            assert torch.equal(x_buf, x)                                # the exchange rebuilt the replica
-            if wt is not None:
-                full = oracle.gather_weight_scatter(src_index, dst, weight, x, reduce)
-            else:
-                full = oracle.gather_scatter(src_index, dst, x, reduce)
-            assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), reduce
-    # needed-rows form: the same schedule carrying only the rows each bucket references
-    pn = gdist.PipelinedGather(shard, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm], needed_only=True)
-    got_rows, full_rows = pn.exchanged_rows()
-    assert 0 <= got_rows <= full_rows
-    nd = pn.needed
-    for k in range(1, world):
-        owner = (rank + k) % world
-        s_k = b.src_index[b.bounds[k]:b.bounds[k + 1]]
-        assert nd.recv_counts[owner] == torch.unique(s_k).numel()
-        c_k = nd.src_index[b.bounds[k]:b.bounds[k + 1]]
-        if c_k.numel():
-            assert int(c_k.min()) >= nd.recv_offsets[k - 1] and int(c_k.max()) < nd.recv_offsets[k]
-    for reduce in ["sum", "mean"]:
-        for wt in (None, weight):
-            for form in ("full_buffer", "own_rows"):
-                if form == "full_buffer":
-                    x_in = torch.full((N, F), float("nan"))
-                    pn.local_rows(x_in).copy_(x_local)
-                else:
-                    x_in = x_local.clone()
-                got = pn(x_in, shard.weight if wt is not None else None, reduce)
-                full = (oracle.gather_weight_scatter(src_index, dst, weight, x, reduce) if wt is not None
-                        else oracle.gather_scatter(src_index, dst, x, reduce))
-                assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), (reduce, form)
-    # sparse referencing: when the edges touch few distinct src rows the exchange shrinks accordingly
-    few = src_index % 7
-    sh2 = gdist.shard_graph(few, dst, None, rank, world, row_bounds=rb, edge_bounds=eb)
-    p2 = gdist.PipelinedGather(sh2, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm], needed_only=True)
-    assert p2.exchanged_rows()[0] <= 7
-    got = p2(x_local.clone(), None, "sum")
-    assert torch.allclose(got, oracle.gather_scatter(few, dst, x, "sum")[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6)
-    # peer-push form: ONE push of the requested rows into slots of the requesters' buffers, two buckets.  The stand-in
-    # pusher ships (slot, row) pairs over gloo and the RECEIVER stores each row where the SENDER's slot says, so the
-    # slot arithmetic (dest_peer / dest_row), the two-way bucket split and its src ids are what is under test.
+        for weighted in (False, True):
+            got = bg(x_local.clone(), shard.weight if weighted else None, reduce)
+            assert torch.allclose(got, expect(reduce, weighted), rtol=1e-5, atol=1e-6), ("allgather", reduce, weighted)
+    buf, _ = bg._buffer([F], x.dtype, x.device)
+    assert torch.equal(buf, x)                                          # the exchange rebuilt the replica
+
+    # push transport: ONE push of the requested rows into slots of the requesters' buffers.  The stand-in pusher ships
+    # (slot, row) pairs over gloo and the RECEIVER stores each row where the SENDER's slot says, so the slot arithmetic
+    # (dest_peer / dest_row) and the compact src ids are what is under test.
     holder = {}
 
-    def pusher(x_mine, rows, dest_peer, dest_row, buf, hdl):
-        pp, ops, inbox = holder["pp"], [], {}
+    def pusher(x_mine, nd, buf, hdl):
+        ops, inbox = [], {}
         for p in range(world):
             if p == rank:
                 continue
-            m = dest_peer == p
+            m = nd.dest_peer == p
             if int(m.sum()):
-                ops.append(dist.P2POp(dist.isend, dest_row[m].contiguous(), p, tag=1))
-                ops.append(dist.P2POp(dist.isend, x_mine[rows[m]].contiguous(), p, tag=2))
-            n = pp.requests.recv_counts[p]
+                ops.append(dist.P2POp(dist.isend, nd.dest_row[m].contiguous(), p, tag=1))
+                ops.append(dist.P2POp(dist.isend, x_mine[nd.send_rows[m]].contiguous(), p, tag=2))
+            n = nd.recv_counts[p]
             if n:
                 inbox[p] = (torch.empty(n, dtype=torch.int64), torch.empty([n] + list(x_mine.shape[1:]), dtype=x_mine.dtype))
                 ops.append(dist.P2POp(dist.irecv, inbox[p][0], p, tag=1))
@@ -159,24 +137,33 @@ def _worker(rank, world, port, q, hub=False):
             assert slots.numel() == torch.unique(slots).numel() and int(slots.max()) < buf.shape[0]
             buf[slots] = data
 
-    kw_push = dict(reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm], pusher=pusher,
+    kw_push = dict(transport="push", reducer=reducer, pusher=pusher,
                    allocator=lambda shape, dtype, device: (torch.full(shape, float("nan"), dtype=dtype), None),
                    barrier=lambda hdl, channel: dist.barrier())
-    pp = holder["pp"] = gdist.PeerPushGather(shard, **kw_push)
-    assert pp.buckets.bounds[0] == 0 and pp.buckets.bounds[2] == shard.num_local_edges
-    for k in range(2):
-        d_k = pp.buckets.dst_index[pp.buckets.bounds[k]:pp.buckets.bounds[k + 1]]
-        assert bool((d_k[1:] >= d_k[:-1]).all())
-    assert pp.exchanged_rows() == pn.exchanged_rows()
+    pp = gdist.BucketedGather(shard, **kw_push)
+    check_buckets(pp)
+    got_rows, full_rows = pp.exchanged_rows()
+    assert 0 <= got_rows <= full_rows
+    nd = pp.needed
+    remote_glob = shard.src_index[pp.buckets.perm.long()][pp.buckets.bounds[1]:]
+    assert got_rows == torch.unique(remote_glob).numel() == nd.recv_offsets[-1]
+    c = pp.buckets.src_index[pp.buckets.bounds[1]:]
+    if c.numel():
+        assert int(c.min()) >= 0 and int(c.max()) < nd.recv_offsets[-1] <= nd.buffer_rows
     for reduce in ["sum", "mean"]:
-        for wt in (None, weight):
+        for weighted in (False, True):
             for _ in range(2):                                          # twice: the buffer is reused across calls
-                got = pp(x_local.clone(), shard.weight if wt is not None else None, reduce)
-            full = (oracle.gather_weight_scatter(src_index, dst, weight, x, reduce) if wt is not None
-                    else oracle.gather_scatter(src_index, dst, x, reduce))
-            assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), ("push", reduce)
+                got = pp(x_local.clone(), shard.weight if weighted else None, reduce)
+            assert torch.allclose(got, expect(reduce, weighted), rtol=1e-5, atol=1e-6), ("push", reduce, weighted)
+    # sparse referencing: when the edges touch few distinct src rows the exchange shrinks accordingly
+    few = src_index % 7
+    sh2 = gdist.shard_graph(few, dst, None, rank, world, row_bounds=rb, edge_bounds=eb)
+    p2 = gdist.BucketedGather(sh2, **kw_push)
+    assert p2.exchanged_rows()[0] <= 7
+    got = p2(x_local.clone(), None, "sum")
+    assert torch.allclose(got, oracle.gather_scatter(few, dst, x, "sum")[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6)
 
-    # the DEFAULT branches of PeerPushGather (torch symmetric memory + abi.push_rows), with those two modules faked:
+    # the DEFAULT branches of the push transport (torch symmetric memory + abi.push_rows), with those two modules faked:
     # symm.empty / rendezvous hand out local buffers with a barrier, abi.push_rows delivers over gloo like `pusher`
     import torch.distributed._symmetric_memory as symm
     from geot_b200 import abi
@@ -193,43 +180,40 @@ def _worker(rank, world, port, q, hub=False):
 
     def fake_push_rows(x_mine, rows, dest_peer, dest_row, bases_ptr, aligned16=True):
         h = [h for h in FakeHandle.live if list(h.buf.shape[1:]) == list(x_mine.shape[1:]) and h.buf.dtype == x_mine.dtype][-1]
-        pusher(x_mine, rows, dest_peer, dest_row, h.buf, None)
+        pusher(x_mine, holder["pd"].needed, h.buf, None)
 
     real = (symm.empty, symm.rendezvous, abi.push_rows)
     symm.empty = lambda shape, dtype=None, device=None: torch.full(list(shape), float("nan"), dtype=dtype)
     symm.rendezvous = lambda t, group: FakeHandle(t)
     abi.push_rows = fake_push_rows
     try:
-        pd = holder["pp"] = gdist.PeerPushGather(shard, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm])
+        pd = holder["pd"] = gdist.BucketedGather(shard, transport="push", reducer=reducer)
         # (a rank with nothing to send skips abi.push_rows on the default path but must still receive in this emulation)
-        if pd.requests.send_rows.numel() == 0:
+        if pd.needed.send_rows.numel() == 0:
             pd._pusher = pusher
         for reduce in ["sum", "mean"]:
             got = pd(x_local.clone(), shard.weight, reduce)
-            full = oracle.gather_weight_scatter(src_index, dst, weight, x, reduce)
-            assert torch.allclose(got, full[rb[rank]:rb[rank + 1]], rtol=1e-5, atol=1e-6), ("push default branches", reduce)
+            assert torch.allclose(got, expect(reduce, True), rtol=1e-5, atol=1e-6), ("push default branches", reduce)
         buf, pb = pd._buffer([F], x_local.dtype, x_local.device)
         assert pb.bases.tolist() == pb.handle.buffer_ptrs and pb.bases.dtype == torch.int64
     finally:
         symm.empty, symm.rendezvous, abi.push_rows = real
 
-    # multi-head rows [N, H, F] with per-head weights [E, H] (mh_spmm) through all three overlapped forms
+    # multi-head rows [N, H, F] with per-head weights [E, H] (mh_spmm) through both transports
     Hh = 3
     xh = torch.rand(N, Hh, 4, generator=g)
     wh = torch.rand(E, Hh, generator=g)
     sh_h = gdist.shard_graph(src_index, dst, wh, rank, world, row_bounds=rb, edge_bounds=eb)
     exp_h = oracle.mh_spmm(src_index, dst, wh, xh)[rb[rank]:rb[rank + 1]]
     xh_local = xh[rb[rank]:rb[rank + 1]].clone()
-    for make in (lambda: gdist.PipelinedGather(sh_h, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm]),
-                 lambda: gdist.PipelinedGather(sh_h, reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm],
-                                               needed_only=True),
-                 lambda: gdist.PeerPushGather(sh_h, **kw_push)):
-        obj = holder["pp"] = make()
+    for make in (lambda: gdist.BucketedGather(sh_h, transport="allgather", reducer=reducer),
+                 lambda: gdist.BucketedGather(sh_h, **kw_push)):
+        obj = make()
         got = obj.aggregate(xh_local, sh_h.weight, "sum")
-        assert torch.allclose(got, exp_h, rtol=1e-5, atol=1e-6), type(obj).__name__
+        assert torch.allclose(got, exp_h, rtol=1e-5, atol=1e-6), obj.transport
 
-    # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): every layer through the pipelined
-    # exchange (both forms), against the plain-torch restatement of the stack on the unsharded graph
+    # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): every layer through the bucketed
+    # exchange (both transports; hidden width != input width: per-shape buffers), against the plain-torch restatement
     from geot_b200 import gnn
     torch.manual_seed(7)                                  # same random weights on every rank
     gcn, sage = gnn.GCN(F, 16, 3), gnn.GraphSAGE(F, 16, 3)
@@ -239,15 +223,11 @@ def _worker(rank, world, port, q, hub=False):
     with torch.no_grad():
         exp_gcn = gnn.reference_forward(gcn, x, src_index, dst, norm)[rb[rank]:rb[rank + 1]]
         exp_sage = gnn.reference_forward(sage, x, src_index, dst)[rb[rank]:rb[rank + 1]]
-        for needed_only in (False, True):
-            kw = dict(reducer=reducer, combiner=combiner, permuter=lambda w, perm: w[perm], needed_only=needed_only)
-            got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=gdist.PipelinedGather(sh_gcn, **kw))
-            assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), ("gcn", needed_only)
-            got = gnn.forward_sharded(sage, x_local, sh_sage, gather=gdist.PipelinedGather(sh_sage, **kw))
-            assert torch.allclose(got, exp_sage, rtol=1e-4, atol=1e-4), ("sage", needed_only)
-        holder["pp"] = gdist.PeerPushGather(sh_gcn, **kw_push)
-        got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=holder["pp"])
-        assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), "gcn push"
+        for kw in (dict(transport="allgather", reducer=reducer), kw_push):
+            got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=gdist.BucketedGather(sh_gcn, **kw))
+            assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), ("gcn", kw["transport"])
+            got = gnn.forward_sharded(sage, x_local, sh_sage, gather=gdist.BucketedGather(sh_sage, **kw))
+            assert torch.allclose(got, exp_sage, rtol=1e-4, atol=1e-4), ("sage", kw["transport"])
     dist.barrier()
     q.put((rank, shard.num_local_edges))
     dist.destroy_process_group()

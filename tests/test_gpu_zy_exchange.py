@@ -1,6 +1,7 @@
-"""GPU parity of the device helpers of the multi-GPU path (geot_b200/csrc/exchange.cu) on ONE GPU, through the C ABI:
-permute_edges (per-edge weights into bucket order; feature rows packed for a peer -- byte moves, bit-exact) and
-combine_partials (bucket partials added in bucket order, mean by degree)."""
+"""GPU parity, on ONE GPU and through the C ABI, of what the multi-GPU path and the host-buffer path are built from:
+permute_edges / push_rows (byte moves, bit-exact), the bucketed reduction options of geot_b200_segment_reduce_ex
+(accumulate, edge_perm, mean_rowptr), the in-kernel zero-fill of rows without edges, the row-pointer transport of
+the host-buffer entry and the resident host graph."""
 import os
 
 import pytest
@@ -12,10 +13,6 @@ if torch.cuda.is_available():
     from geot_b200 import abi
 
 DEV = "cuda"
-EXPERIMENT = pytest.mark.skipif(os.environ.get("GEOT_B200_TEST_EXPERIMENTS") != "1",
-                                reason="opt-in feature built after the round's GPU budget was spent, never run on hardware yet: "
-                                       "enable with GEOT_B200_TEST_EXPERIMENTS=1 (scripts/gpu_r02_single.sh does)")
-
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
 @pytest.mark.parametrize("width", [1, 2, 3, 4, 8, 12, 32, 64, 65, 128, 256])
@@ -43,30 +40,6 @@ def test_permute_edges_empty():
     assert got.shape == (0, 4)
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.float64, 1e-12), (torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
-@pytest.mark.parametrize("n_parts", [1, 2, 3, 8])
-@pytest.mark.parametrize("W", [1, 7, 64, 128])
-def test_combine_partials(dtype, tol, n_parts, W):
-    g = torch.Generator().manual_seed(n_parts * 1000 + W)
-    S = 777
-    parts = (torch.rand(n_parts, S, W, generator=g) + 0.5).to(dtype)
-    deg = torch.randint(0, 5, (S,), generator=g)
-    rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)])
-    acc = parts.double().sum(0)
-    for reduce in ("sum", "mean"):
-        out = torch.empty(S, W, dtype=dtype, device=DEV)
-        abi.combine_partials(parts.to(DEV), out, reduce, rowptr.to(DEV) if reduce == "mean" else None)
-        exp = acc if reduce == "sum" else acc / deg.clamp_min(1).double().unsqueeze(-1)
-        assert ((out.cpu().double() - exp).abs() <= tol * exp.abs()).all(), (reduce, n_parts, W)
-    if dtype in (torch.float32, torch.float64):      # bucket order is the summation order: bit-exact against it
-        seq = parts[0].clone()
-        for q in range(1, n_parts):
-            seq = seq + parts[q]
-        out = torch.empty(S, W, dtype=dtype, device=DEV)
-        abi.combine_partials(parts.to(DEV), out, "sum", None)
-        assert torch.equal(out.cpu(), seq)
-
-
 def test_debug_mode_checks_src_index_range(monkeypatch):
     """src_index is unchecked on the fast path (as in the reference); GEOT_B200_DEBUG=1 checks it."""
     import geot_b200
@@ -83,14 +56,11 @@ def test_debug_mode_checks_src_index_range(monkeypatch):
         geot_b200.gather_weight_scatter(bad - 11, di, torch.rand(4, device=DEV), x)
 
 
-@EXPERIMENT
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("width", [2, 6, 8, 64, 128, 130])
+@pytest.mark.parametrize("width", [2, 3, 6, 8, 64, 128, 130])
 def test_push_rows_into_peer_buffers(dtype, width):
     """geot_b200_push_rows on one GPU: the "peers" are three local buffers whose base pointers sit in a device array,
     exactly as symmetric memory presents the mapped buffers of the other GPUs.  Byte moves: bit-exact."""
-    if width * torch.tensor([], dtype=dtype).element_size() % 4:
-        pytest.skip("rows are moved in 4-byte words")
     g = torch.Generator().manual_seed(width)
     n_in, n = 500, 2000
     x = torch.rand(n_in, width, generator=g).to(dtype).to(DEV)
@@ -111,11 +81,11 @@ def test_push_rows_into_peer_buffers(dtype, width):
         assert torch.equal(bufs[p].cpu(), exp)
 
 
-@EXPERIMENT
-@pytest.mark.parametrize("mask", [1, 2, 3])
-def test_host_entry_compact_transport(monkeypatch, mask):
-    """GEOT_B200_HOST_COMPACT: row pointers instead of dst_index (1), int32 src_index (2) over the link.  Same slices,
-    same kernels, same edge partition => bit-identical to the plain transport; fewer bytes moved."""
+@pytest.mark.parametrize("mask", [1])
+def test_host_entry_row_pointer_transport(monkeypatch, mask):
+    """The host entry's default transport sends each slice's row pointers instead of its dst_index
+    (GEOT_B200_HOST_COMPACT=0 sends the operands as given).  Same slices, same kernels, same edge partition =>
+    bit-identical results; fewer bytes moved."""
     import oracle
     g = torch.Generator().manual_seed(mask)
     E, N, F = 300000, 900, 64
@@ -143,61 +113,125 @@ def test_host_entry_compact_transport(monkeypatch, mask):
             assert torch.equal(got, plain[i]), (mask, threads, i)
             h2d, d2h = abi.host_last_transfer()
             assert d2h == moved[i][1]
-            if (mask & 1) or s_i is not None:
-                assert h2d < moved[i][0], (mask, i, h2d, moved[i][0])
+            assert h2d < moved[i][0], (mask, i, h2d, moved[i][0])
     assert abi.lib().geot_b200_host_arena_release() == 0
 
 
-@EXPERIMENT
-@pytest.mark.parametrize("dtype,F", [(torch.float32, 64), (torch.float32, 7), (torch.bfloat16, 24), (torch.float64, 3)])
-def test_zero_only_the_empty_rows(monkeypatch, dtype, F):
-    """GEOT_B200_ZERO_EMPTY=1: with a plan, rows without edges are zero-filled one by one instead of a memset of the
-    whole output.  Same result bit for bit, on a graph with runs of empty rows, a dirty output buffer and S beyond the
-    plan's last row."""
-    g = torch.Generator().manual_seed(F)
+@pytest.mark.parametrize("dtype,F", [(torch.float32, 64), (torch.float32, 7), (torch.float32, 128), (torch.float32, 300),
+                                     (torch.bfloat16, 24), (torch.float64, 3)])
+@pytest.mark.parametrize("chunk", [0, 8, 64])
+def test_rows_without_edges_are_zero_filled_in_kernel(monkeypatch, dtype, F, chunk):
+    """No memset of dst (the reference clears all of it first, csrc/gather_scatter.cpp:27-30): the group that sees a
+    jump in the sorted index zero-fills the rows in between.  Dirty output buffer, runs of empty rows at the start,
+    in the middle (longer than a chunk's rows) and at the end, S beyond the last index, with and without a plan,
+    every reduce op."""
+    import oracle
+    monkeypatch.setenv("GEOT_B200_CHUNK", str(chunk))
+    g = torch.Generator().manual_seed(F + chunk)
     N, E = 3000, 20000
     wdeg = torch.rand(N, generator=g) ** 3
-    wdeg[100:400] = 0                                            # a run of empty rows
+    wdeg[:17] = 0                                                # leading empty rows
+    wdeg[100:400] = 0                                            # a long run of empty rows
     wdeg[::7] = 0                                                # scattered empty rows
-    di = torch.multinomial(wdeg / wdeg.sum(), E, replacement=True, generator=g).sort().values.to(DEV)
-    si = torch.randint(0, N, (E,), generator=g).to(DEV)
-    x = torch.rand(N, F, generator=g).to(dtype).to(DEV)
+    wdeg[N - 9:] = 0                                             # trailing empty rows (below S)
+    di_c = torch.multinomial(wdeg / wdeg.sum(), E, replacement=True, generator=g).sort().values
+    si_c = torch.randint(0, N, (E,), generator=g)
+    x_c = (torch.rand(N, F, generator=g) + 0.5).to(dtype)
+    di, si, x = di_c.to(DEV), si_c.to(DEV), x_c.to(DEV)
     plan = abi.DevicePlan(di)
-    assert plan.c.has_gaps == 1
-    for S in (plan.S, plan.S + 37):
-        outs = []
-        for flag in ("0", "1"):
-            monkeypatch.setenv("GEOT_B200_ZERO_EMPTY", flag)
-            out = torch.full((S, F), 7.0, dtype=dtype, device=DEV)           # dirty: stale values must not survive
-            abi.segment_reduce(x, si, di, None, "sum", S=S, plan=plan, out=out)
-            outs.append(out.clone())
-        assert torch.equal(outs[0], outs[1])
-        deg = torch.bincount(di.cpu(), minlength=S)
-        assert bool((outs[1].cpu()[deg == 0] == 0).all())
+    assert plan.c.has_gaps == 1 and plan.c.max_row == int(di_c[-1])
+    for S in (plan.S, N, N + 37):
+        deg = torch.bincount(di_c, minlength=S)
+        for reduce in ("sum", "mean", "max", "min"):
+            exp = oracle.segment_reduce(x_c, si_c, di_c, None, reduce, S=S)
+            for pl in (plan, None):
+                out = torch.full((S, F), 7.0, dtype=dtype, device=DEV)       # dirty: stale values must not survive
+                abi.segment_reduce(x, si, di, None, reduce, S=S, plan=pl, out=out)
+                got = out.cpu()
+                assert bool((got[deg == 0] == 0).all()), (S, reduce, pl is None)
+                tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+                assert torch.allclose(got.double(), exp.double(), rtol=tol, atol=1e-6), (S, reduce, pl is None)
 
 
-@EXPERIMENT
-def test_lean_register_path_bit_identical_and_vs_oracle(monkeypatch):
-    """GEOT_B200_RING=96, the lean register path (experiment, fp32 rows of 256 B - 1 KB; other shapes fall back to
-    the lean ring): walks a chunk in the same order as every other variant, so sums must be bit-identical to the
-    register path (ring 0), and it is checked against the oracle.  Same graphs as the ring-variant test."""
+@pytest.mark.parametrize("dtype,F", [(torch.float32, 128), (torch.float32, 64), (torch.float32, 5), (torch.bfloat16, 64),
+                                     (torch.float64, 16)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_bucketed_passes_accumulate_perm_mean(monkeypatch, dtype, F, weighted):
+    """geot_b200_segment_reduce_ex: the edge list split stably into two dst-sorted buckets (as dist.BucketedGather
+    splits it into src-local / src-remote); pass 1 writes every row, pass 2 runs with accumulate, both read the
+    caller's weights through edge_perm, mean divides by the degree in the COMPLETE list.  Must equal the one-pass
+    result within the sum tolerance, for hub rows cut by many tiles as well."""
     import oracle
-    from test_gpu_parity import assert_close, make_graph, run_abi
-    graphs = [(40000 + 37, 60, 0.2, 0.0, 64), (30000 + 5, 9000, 0.0, 0.0, 32), (65536, 500, 0.6, 0.4, 128), (4099, 40, 0.0, 0.0, 256),
-              (200000 + 3, 700, 0.3, 0.2, 0)]
-    for gi, (E, N, skew, hub, chunk) in enumerate(graphs):
+    g = torch.Generator().manual_seed(F)
+    N, E = 1200, 150000
+    wdeg = torch.rand(N, generator=g) ** 4
+    wdeg[N // 2] = 0.4 * float(wdeg.sum())                       # hub row: crosses tiles -> fixup path accumulates too
+    wdeg[3:30] = 0
+    di_c = torch.multinomial(wdeg / wdeg.sum(), E, replacement=True, generator=g).sort().values
+    si_c = torch.randint(0, N, (E,), generator=g)
+    w_c = (torch.rand(E, generator=g) + 0.25).to(dtype) if weighted else None
+    x_c = (torch.rand(N, F, generator=g) + 0.5).to(dtype)
+    S = N
+    key = (si_c >= N // 3).to(torch.int8)                        # "remote" = src row in the upper two thirds
+    perm_c = torch.argsort(key, stable=True)
+    n0 = int((key == 0).sum())
+    di, si = di_c[perm_c].to(DEV), si_c[perm_c].to(DEV)
+    perm32 = perm_c.to(torch.int32).to(DEV)
+    x = x_c.to(DEV)
+    w = w_c.to(DEV) if weighted else None
+    deg = torch.bincount(di_c, minlength=S)
+    rowptr = torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)]).to(DEV)
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    for chunk in (0, 16):
         monkeypatch.setenv("GEOT_B200_CHUNK", str(chunk))
-        si, di, g = make_graph(E, N, seed=100 * gi + 96, skew=skew, hub=hub, gaps=(gi == 1))
-        w = torch.rand(E, generator=g) + 0.25
-        for F in (32, 64, 100, 128, 256, 512):
-            src = torch.rand(N, F, generator=g)
-            for name, (a_si, a_w, a_src) in {"index_scatter": (None, None, src[si]), "gather_scatter": (si, None, src),
-                                             "gather_weight_scatter": (si, w, src)}.items():
-                for reduce in ("sum", "mean"):
-                    monkeypatch.setenv("GEOT_B200_RING", "0")
-                    base = run_abi(a_src, a_si, di, a_w, reduce)
-                    monkeypatch.setenv("GEOT_B200_RING", "96")
-                    got = run_abi(a_src, a_si, di, a_w, reduce)
-                    what = "%s %s ring=96 F=%d graph=%d" % (name, reduce, F, gi)
-                    assert torch.equal(got, base), what
-                    assert_close(got, oracle.segment_reduce(a_src, a_si, di, a_w, reduce, acc64=True), torch.float32, reduce, what)
+        for reduce in ("sum", "mean"):
+            out = torch.full((S, F), 3.0, dtype=dtype, device=DEV)
+            mr = rowptr if reduce == "mean" else None
+            for (a, b, acc) in ((0, n0, False), (n0, E, True)):
+                plan = abi.DevicePlan(di[a:b], S)
+                abi.segment_reduce(x, si[a:b], di[a:b], w, reduce, S=S, plan=plan, out=out, accumulate=acc,
+                                   edge_perm=perm32[a:b] if weighted else None, mean_rowptr=mr)
+            exp = oracle.segment_reduce(x_c, si_c, di_c, w_c, reduce, S=S, acc64=(dtype == torch.float32))
+            assert torch.allclose(out.cpu().double(), exp.double(), rtol=tol, atol=1e-6), (reduce, chunk)
+    # what the options do not serve is refused, not mis-computed
+    with pytest.raises(abi.AbiError):
+        abi.segment_reduce(x, si, di, None, "max", S=S, accumulate=True)
+    with pytest.raises(abi.AbiError):
+        abi.segment_reduce(x, si, di, None, "mean", S=S, accumulate=True)          # mean needs mean_rowptr
+
+
+def test_resident_host_graph_matches_stateless_host_entry():
+    """geot_b200_host_graph_*: indices uploaded once, per call only src + weights in and dst out.  Same kernels on
+    the same slices of the edge list as far as the sums are concerned: equal to the oracle within the sum tolerance,
+    bit-exact for max; the bytes per call exclude the index arrays."""
+    import oracle
+    g = torch.Generator().manual_seed(5)
+    E, N, F = 400000, 900, 64
+    w_deg = torch.rand(N, generator=g) ** 3
+    w_deg[N // 3] = 0.3 * float(w_deg.sum())
+    w_deg[5:40] = 0
+    di = torch.multinomial(w_deg / w_deg.sum(), E, replacement=True, generator=g).sort().values.contiguous()
+    si = torch.randint(0, N, (E,), generator=g)
+    S = int(di[-1]) + 1 + 4
+    x = torch.rand(N, F, generator=g)
+    xe = torch.rand(E, 24, generator=g)
+    hg = abi.HostGraph(si, di, S, N)
+    for it in range(2):                                          # weights / features change from call to call
+        w = torch.rand(E, generator=g)
+        x = x + it
+        got = hg.reduce(x, w, "sum")
+        assert torch.allclose(got, oracle.segment_reduce(x, si, di, w, "sum", S=S, acc64=True), rtol=1e-5, atol=1e-6)
+        h2d, d2h, resident = hg.last_transfer()
+        assert h2d == x.numel() * 4 + E * 4 and d2h == S * F * 4 and resident == 2 * E * 8
+    assert torch.equal(hg.reduce(x, None, "max"), oracle.segment_reduce(x, si, di, None, "max", S=S))
+    got = hg.reduce(x, None, "mean")
+    assert torch.allclose(got, oracle.segment_reduce(x, si, di, None, "mean", S=S), rtol=1e-5, atol=1e-6)
+    wh = torch.rand(E, 4, generator=g).bfloat16()
+    xh = torch.rand(N, 4, 16, generator=g).bfloat16()
+    got = hg.reduce(xh, wh, "sum", H=4)
+    assert torch.allclose(got.float(), oracle.segment_reduce(xh, si, di, wh, "sum", S=S, H=4).float(), rtol=1e-2, atol=1e-2)
+    hg.close()
+    hi = abi.HostGraph(None, di, S, 0)                           # index_scatter: src rows are edge-aligned
+    got = hi.reduce(xe, None, "sum")
+    assert torch.allclose(got, oracle.segment_reduce(xe, None, di, None, "sum", S=S, acc64=True), rtol=1e-5, atol=1e-6)
+    hi.close()

@@ -152,41 +152,3 @@ def test_pattern_transform_rewrites_message_passing_chains():
     assert any("index_add" in t for t in targets) and not any("geot" in t for t in targets)
     x = torch.rand(3, 4)
     assert torch.equal(torch.ops.geot.pad_rows(x, 5)[:3], x) and torch.ops.geot.pad_rows(x, 5)[3:].abs().sum() == 0
-
-
-def test_src_blocked_gather_host_logic():
-    """SrcBlockedGather (single-GPU L2 blocking experiment): bucketing by src row range, bucket order, combine.  The
-    device kernels are replaced by CPU stand-ins (the oracle as the checker), as in the gloo tests."""
-    import oracle
-    from geot_b200 import dist as gdist
-    g = torch.Generator().manual_seed(3)
-    N, E, F = 257, 9000, 10
-    dst = torch.multinomial(torch.rand(N, generator=g) ** 3, E, replacement=True, generator=g).sort().values
-    src = torch.randint(0, N, (E,), generator=g)
-    w = torch.rand(E, generator=g)
-    x = torch.rand(N, F, generator=g)
-    S = int(dst[-1]) + 1
-
-    def reducer(xf, si, di, ww, S_):
-        return oracle.segment_reduce(xf, si, di, ww, "sum", S=S_)
-
-    def combiner(parts, reduce, dst_local, S_):
-        tot = parts.sum(0)
-        if reduce == "mean":
-            tot = tot / torch.bincount(dst_local, minlength=S_).clamp_min(1).to(tot.dtype).unsqueeze(-1)
-        return tot
-
-    for blocks in (1, 2, 3, 8):
-        bg = gdist.SrcBlockedGather(src, dst, S, N, blocks, reducer=reducer, combiner=combiner, permuter=lambda t, p: t[p])
-        b = bg.buckets
-        assert b.bounds[0] == 0 and b.bounds[-1] == E and len(b.bounds) == blocks + 1
-        per = (N + blocks - 1) // blocks
-        for k in range(blocks):
-            s_k = b.src_index[b.bounds[k]:b.bounds[k + 1]]
-            d_k = b.dst_index[b.bounds[k]:b.bounds[k + 1]]
-            assert bool(((s_k >= k * per) & (s_k < (k + 1) * per)).all()) and bool((d_k[1:] >= d_k[:-1]).all())
-        for reduce in ("sum", "mean"):
-            assert torch.allclose(bg(x, w, reduce), oracle.gather_weight_scatter(src, dst, w, x, reduce), rtol=1e-5, atol=1e-6)
-            assert torch.allclose(bg(x, None, reduce), oracle.gather_scatter(src, dst, x, reduce), rtol=1e-5, atol=1e-6)
-        wp = bg.permute_weight(w)
-        assert torch.allclose(bg(x, wp, "sum", permuted=True), oracle.gather_weight_scatter(src, dst, w, x, "sum"), rtol=1e-5, atol=1e-6)

@@ -1,6 +1,6 @@
 """BASELINE configs[4] at N GPUs: 3-layer GCN / GraphSAGE forward on the synthetic proteins-shape graph
 (132,534 nodes, 39.5 M edges, in = hidden = out = 256, fp32), node rows sharded by dst row over the GPUs of one box,
-through every form of the src-row exchange.  One process per GPU:
+through every form of the src-row exchange (one all-gather per layer / bucketed all-gather / bucketed push).  One process per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 \
         scripts/bench_model_multi.py > gpurun_out/<tag>/model_nN.jsonl
@@ -61,10 +61,9 @@ def main():
             exp = full[rb[rank]:rb[rank + 1]]
             rec = {"model": "3-layer %s forward, proteins shape, 256-256-256-256, fp32" % name, "N": N, "E": E, "n_gpus": world,
                    "shard_imbalance": round(shard.imbalance, 4), "single_gpu_ms": single}
-            for form in ("allgather", "pipeline", "needed", "push"):
+            for form in ("allgather", "bucket", "push"):
                 try:
-                    gather = (None if form == "allgather" else gdist.PeerPushGather(shard) if form == "push"
-                              else gdist.PipelinedGather(shard, needed_only=(form == "needed")))
+                    gather = None if form == "allgather" else gdist.BucketedGather(shard, transport="push" if form == "push" else "allgather")
                     got = gnn.forward_sharded(model, x_local, shard, gather=gather)
                     err = float(((got - exp).abs() / exp.abs().clamp_min(1e-3)).max()) if got.numel() else 0.0
                     rec[form + "_ms"] = timed(lambda: gnn.forward_sharded(model, x_local, shard, gather=gather))

@@ -1,0 +1,54 @@
+#!/bin/bash
+# One parametrised GPU session (replaces the per-session scripts of round 1).  Every leg writes its own file under
+# gpurun_out/<tag>/ as soon as it ends.
+#   gpurun [--gpus N] --timeout T -- 'bash scripts/gpu_session.sh <tag> <legs...>'
+# legs: test (pytest -m gpu) | smoke | bench (default bench.py, own + reference arm) | benchN (torchrun bench at N = all
+#       visible GPUs, own + reference arm) | exch (N > 1: products / reddit with every exchange form) | model (configs[4]
+#       at N GPUs) | launches (ncu launch list of the default bench) | ncu:<workload> (one --set full capture) |
+#       tune:<workload>[:chunks] | env:<NAME=VALUE> (exported for the legs that follow)
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+N=$(nvidia-smi -L | wc -l)
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem --format=csv > $OUT/gpu.txt 2>&1
+trun() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 "$@"; }
+for leg in "$@"; do
+  echo "== leg $leg ($(date +%T))"
+  case $leg in
+    env:*) export "${leg#env:}";;
+    test) timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -25 | tee $OUT/pytest_gpu.txt;;
+    smoke) timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee $OUT/smoke.txt;;
+    bench)
+      timeout 900 python bench.py --impl reference 2>$OUT/bench_reference.err | tail -1 > $OUT/bench_reference.json
+      timeout 900 python bench.py 2>$OUT/bench.err | tail -1 > $OUT/bench.json
+      tail -3 $OUT/bench.err; cut -c1-600 $OUT/bench.json;;
+    benchN)
+      timeout 600 trun bench.py --gpus $N --impl reference 2>$OUT/bench_n${N}_reference.err | tail -1 > $OUT/bench_n${N}_reference.json
+      timeout 900 trun bench.py --gpus $N 2>$OUT/bench_n$N.err | tail -1 > $OUT/bench_n$N.json
+      tail -3 $OUT/bench_n$N.err; cut -c1-600 $OUT/bench_n$N.json;;
+    exch)
+      for wl in reddit_gws products_gs64; do for ex in bucket push allgather replicated; do
+        GEOT_B200_BENCH_SECONDARY=0 GEOT_B200_EXCHANGE=$ex timeout 300 trun bench.py --gpus $N --workload $wl --steps 10 --warmup 3 \
+          2>$OUT/exch_${wl}_$ex.err | tail -1 > $OUT/exch_${wl}_$ex.json
+        python - <<PY
+import json
+try:
+    d = json.load(open("$OUT/exch_${wl}_$ex.json"))
+    print("$wl $ex N=$N: %.4f ms/step, kernel %.4f ms, parity %s, e2e %.3f ms" % (d["ms_per_step"], d["roofline"]["kernel_ms"], d["parity"]["ok"], d["e2e"].get("ms_per_step", -1)))
+except Exception as e:
+    print("$wl $ex N=$N: FAILED", e)
+PY
+      done; done 2>&1 | tee $OUT/exch.txt;;
+    model) timeout 600 trun scripts/bench_model_multi.py > $OUT/model_n$N.jsonl 2> $OUT/model_n$N.err; cut -c1-900 $OUT/model_n$N.jsonl; tail -3 $OUT/model_n$N.err;;
+    launches)
+      GEOT_B200_BENCH_SECONDARY=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+        python bench.py --steps 3 --warmup 3 > $OUT/bench_under_ncu.log 2>&1; grep -c geot $OUT/launches.csv;;
+    ncu:*) wl=${leg#ncu:}
+      GEOT_B200_BENCH_SECONDARY=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:segment_reduce_kernel -s 3 -c 1 -o $OUT/prof_$wl \
+        python bench.py --workload $wl --steps 3 --warmup 3 > $OUT/prof_$wl.log 2>&1; ls -la $OUT/prof_$wl.ncu-rep;;
+    tune:*) IFS=: read -r _ wl chunks <<< "$leg"
+      timeout 300 python scripts/tune.py $wl ${chunks:-0} 2>&1 | grep -E "lib=|rror" | tee -a $OUT/tune.txt;;
+    *) echo "unknown leg $leg";;
+  esac
+done
+ls -la $OUT

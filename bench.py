@@ -311,11 +311,20 @@ class Runner:
         self.E = self.di.numel()
         self.W = wk["F"] * H
         self.out = torch.empty([self.S] + tail, dtype=wk["dtype"], device=dev)
-        self.plan = self.ws = None
+        self.plan = self.ws = self.blocks = None
         if self.bg is None and self.E > 0:
             self.plan = abi.DevicePlan(self.di, self.S)
-            self.ws = abi.Workspace(self.E, self.W, wk["dtype"], dev)
-        self.calls_per_step = 2 if self.bg is not None else 1
+            # src-row blocking for the L2 (built once per graph, like the plan): the library's own suggestion unless
+            # GEOT_B200_SRC_BLOCKS forces a count (1 = off)
+            nb = int(os.environ.get("GEOT_B200_SRC_BLOCKS", "0"))
+            if self.gather and H == 1 and self.exchange in ("none", "replicated"):
+                if nb <= 0:
+                    nb = abi.src_blocks_suggest(self.E, self.S, wk["N"], self.W * wk["esize"])
+                if nb > 1:
+                    self.blocks = abi.SrcBlocks(self.si, self.di, wk["N"], nb)
+            self.ws = abi.Workspace(self.E, self.W, wk["dtype"], dev, src_blocks=self.blocks)
+        self.n_blocks = self.blocks.n_blocks if self.blocks is not None else 1
+        self.calls_per_step = 2 if self.bg is not None else self.n_blocks
         per_head_perm = 1 if (self.bg is not None and w is not None and w.dim() == 2) else 0
         # this library's kernels per step: main + fixup per reduction (+ the push kernel, + the per-head weight permutation)
         self.launches_per_step = 2 * self.calls_per_step + (1 if self.exchange == "push" else 0) + per_head_perm
@@ -333,7 +342,8 @@ class Runner:
             # the timed step reads the pre-replicated matrix; any other operand (the parity check's) is gathered afresh
             x = self.x_full if x is self.x_local else self.gdist.all_gather_rows(x, self.shard.row_bounds)
         return abi.segment_reduce(x, self.si, self.di, w, reduce, S=self.S, H=wk["H"], weight_layout=self.layout if w is not None else abi.W_NONE,
-                                  plan=self.plan, out=out, workspace=self.ws)
+                                  plan=self.plan, out=out, workspace=self.ws,
+                                  src_blocks=self.blocks if reduce in ("sum", "mean") else None)
 
     def src_operand(self):
         if self.world == 1:
@@ -478,7 +488,7 @@ def summarize(wk, r, ms, kmean, peak, parity, world):
          "edges_per_s": wk["E"] / (ms * 1e-3), "kernel_ms": round(kmean, 4), "kernel_achieved_gbs": round(achieved, 1),
          "frac_of_measured_hbm": round(wk["bytes_logical"] / (ms * 1e-3) / 1e9 / peak, 4),
          "bytes_logical_per_step": wk["bytes_logical"], "bytes_compulsory_per_step": wk["bytes_compulsory"],
-         "traffic": traffic, "exchange": r.exchange, "parity": parity}
+         "traffic": traffic, "exchange": r.exchange, "src_blocks": r.n_blocks, "parity": parity}
     d.update(f)
     return d
 
@@ -650,7 +660,10 @@ def run_own(args):
                         "frac_logical can exceed 1 and is NOT an HBM fraction: frac_dram (ncu dram bytes / kernel time) is what "
                         "the DRAM interface carried, frac_compulsory what it had to carry at least (%d bytes per launch)" % k_comp}
     roofline.update(fr)
-    meta = dict(metric=metric_name(wk), dtype=DTYPE_NAME[wk["dtype"]], config=config_of(wk, world, r.exchange), E=wk["E"],
+    cfg = config_of(wk, world, r.exchange)
+    cfg["src_blocks"] = ("%d (the edge list regrouped once per graph by src-row block for the L2; one pass per block, later passes "
+                         "accumulate)" % r.n_blocks) if r.n_blocks > 1 else "1 (one pass)"
+    meta = dict(metric=metric_name(wk), dtype=DTYPE_NAME[wk["dtype"]], config=cfg, E=wk["E"],
                 launches=r.launches_per_step, exchange=r.exchange, imbalance=r.imbalance, exchanged=r.exchanged)
 
     n_e2e = max(3, min(args.steps, 5))

@@ -27,7 +27,8 @@ SYMBOLS = [
     "geot_b200_l2_persist", "geot_b200_l2_persist_reset", "geot_b200_push_rows",
     "geot_b200_host_last_transfer", "geot_b200_host_row_pointers", "geot_b200_segment_reduce_ex",
     "geot_b200_host_graph_create", "geot_b200_host_graph_reduce", "geot_b200_host_graph_last_transfer",
-    "geot_b200_host_graph_destroy",
+    "geot_b200_host_graph_destroy", "geot_b200_src_blocks_suggest", "geot_b200_src_blocks_bytes",
+    "geot_b200_src_blocks_scratch_bytes", "geot_b200_src_blocks_build", "geot_b200_src_blocks_workspace_bytes",
 ]
 
 
@@ -37,10 +38,20 @@ class GeotPlan(ctypes.Structure):
                 ("rowptr", ctypes.c_void_p), ("max_row", ctypes.c_int64)]
 
 
+MAX_SRC_BLOCKS = 16
+
+
+class SrcBlocksC(ctypes.Structure):
+    """geot_src_blocks_t."""
+    _fields_ = [("E", ctypes.c_int64), ("n_blocks", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("bounds", ctypes.c_int64 * (MAX_SRC_BLOCKS + 1)), ("dst_index", ctypes.c_void_p),
+                ("src_index", ctypes.c_void_p), ("edge_perm", ctypes.c_void_p)]
+
+
 class ReduceOpts(ctypes.Structure):
     """geot_reduce_opts_t (geot_b200_segment_reduce_ex)."""
     _fields_ = [("struct_size", ctypes.c_size_t), ("accumulate", ctypes.c_int32), ("reserved", ctypes.c_int32),
-                ("edge_perm", ctypes.c_void_p), ("mean_rowptr", ctypes.c_void_p)]
+                ("edge_perm", ctypes.c_void_p), ("mean_rowptr", ctypes.c_void_p), ("src_blocks", ctypes.POINTER(SrcBlocksC))]
 
 
 _lib = None
@@ -73,6 +84,14 @@ def lib() -> ctypes.CDLL:
         ull = ctypes.POINTER(ctypes.c_ulonglong)
         L.geot_b200_host_graph_last_transfer.argtypes = [vp, ull, ull, ull]
         L.geot_b200_host_graph_destroy.argtypes = [vp]
+        L.geot_b200_src_blocks_suggest.argtypes = [i64, i64, i64, i64]
+        L.geot_b200_src_blocks_bytes.restype = sz
+        L.geot_b200_src_blocks_bytes.argtypes = [i64]
+        L.geot_b200_src_blocks_scratch_bytes.restype = sz
+        L.geot_b200_src_blocks_scratch_bytes.argtypes = [i64]
+        L.geot_b200_src_blocks_build.argtypes = [vp, vp, i64, i64, ci, vp, sz, vp, sz, ctypes.POINTER(SrcBlocksC), vp]
+        L.geot_b200_src_blocks_workspace_bytes.restype = sz
+        L.geot_b200_src_blocks_workspace_bytes.argtypes = [ctypes.POINTER(SrcBlocksC), i64, ci]
         L.geot_b200_index_scatter.argtypes = [vp, vp, vp, i64, i64, i64, ci, ci, ci, ctypes.POINTER(GeotPlan), vp, sz, vp]
         L.geot_b200_gather_scatter.argtypes = [vp, vp, vp, vp, i64, i64, i64, ci, ci, ctypes.POINTER(GeotPlan), vp, sz, vp]
         L.geot_b200_gather_weight_scatter.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, ci, ci,
@@ -164,17 +183,44 @@ class DevicePlan:
 
 
 class Workspace:
-    def __init__(self, E, W, dtype, device, sorted=True):
+    def __init__(self, E, W, dtype, device, sorted=True, src_blocks=None):
         n = lib().geot_b200_workspace_bytes(E, W, DTYPE[dtype], 1 if sorted else 0)
+        if src_blocks is not None:      # every block partitions on its own
+            n = max(n, lib().geot_b200_src_blocks_workspace_bytes(ctypes.byref(src_blocks.c), W, DTYPE[dtype]))
         self.buf = torch.empty(n, dtype=torch.uint8, device=device)
         self.nbytes = n
 
 
+def src_blocks_suggest(E: int, S: int, N_src: int, row_bytes: int) -> int:
+    """Number of src-row blocks worth using for this shape (1: do not block) -- geot_b200_src_blocks_suggest."""
+    return int(lib().geot_b200_src_blocks_suggest(E, S, N_src, row_bytes))
+
+
+class SrcBlocks:
+    """The edge list regrouped by src-row block for the L2 (geot_b200_src_blocks_build); owns its device buffer."""
+
+    def __init__(self, src_index: torch.Tensor, dst_index: torch.Tensor, N_src: int, n_blocks: int):
+        L = lib()
+        E = dst_index.numel()
+        nbytes, sbytes = L.geot_b200_src_blocks_bytes(E), L.geot_b200_src_blocks_scratch_bytes(E)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dst_index.device)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=dst_index.device)
+        self.c = SrcBlocksC()
+        check(L.geot_b200_src_blocks_build(_ptr(src_index), _ptr(dst_index), E, N_src, n_blocks, _ptr(self.buf), nbytes,
+                                           _ptr(scratch), sbytes, ctypes.byref(self.c), _stream()), "src_blocks_build")
+        self.n_blocks = n_blocks
+        self.bounds = [int(self.c.bounds[i]) for i in range(n_blocks + 1)]
+        a = (E * 8 + 255) // 256 * 256
+        self.dst_index = self.buf[:E * 8].view(torch.int64)
+        self.src_index = self.buf[a:a + E * 8].view(torch.int64)
+        self.edge_perm = self.buf[2 * a:2 * a + E * 4].view(torch.int32)
+
+
 def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H=1, weight_layout=None,
                    sorted=True, plan: DevicePlan = None, out=None, workspace: Workspace = None,
-                   accumulate=False, edge_perm=None, mean_rowptr=None):
+                   accumulate=False, edge_perm=None, mean_rowptr=None, src_blocks: "SrcBlocks" = None):
     """Device-pointer call of geot_b200_segment_reduce (geot_b200_segment_reduce_ex when one of ``accumulate`` /
-    ``edge_perm`` [E] int32 / ``mean_rowptr`` [S+1] int64 is given).  Returns dst [S, W]."""
+    ``edge_perm`` [E] int32 / ``mean_rowptr`` [S+1] int64 / ``src_blocks`` is given).  Returns dst [S, W]."""
     E = dst_index.numel()
     W = src.numel() // src.shape[0]
     F = W // H
@@ -185,16 +231,17 @@ def segment_reduce(src, src_index, dst_index, weight, reduce="sum", *, S=None, H
     if out is None:
         out = torch.empty([S] + list(src.shape[1:]), dtype=src.dtype, device=src.device)
     if workspace is None:
-        workspace = Workspace(E, W, src.dtype, src.device, sorted)
+        workspace = Workspace(E, W, src.dtype, src.device, sorted, src_blocks)
     args = (_ptr(src), _ptr(src_index), _ptr(dst_index), _ptr(weight), _ptr(out), E, S, H, F, DTYPE[src.dtype],
             REDUCE[reduce], weight_layout, 1 if sorted else 0, ctypes.byref(plan.c) if plan is not None else None,
             _ptr(workspace.buf), workspace.nbytes, _stream())
-    if accumulate or edge_perm is not None or mean_rowptr is not None:
+    if accumulate or edge_perm is not None or mean_rowptr is not None or src_blocks is not None:
         assert edge_perm is None or (edge_perm.dtype == torch.int32 and edge_perm.numel() == E)
         assert mean_rowptr is None or (mean_rowptr.dtype == torch.int64 and mean_rowptr.numel() == S + 1)
         opts = ReduceOpts(ctypes.sizeof(ReduceOpts), 1 if accumulate else 0, 0,
                           edge_perm.data_ptr() if edge_perm is not None else None,
-                          mean_rowptr.data_ptr() if mean_rowptr is not None else None)
+                          mean_rowptr.data_ptr() if mean_rowptr is not None else None,
+                          ctypes.pointer(src_blocks.c) if src_blocks is not None else None)
         st = lib().geot_b200_segment_reduce_ex(*args, ctypes.byref(opts))
     else:
         st = lib().geot_b200_segment_reduce(*args)

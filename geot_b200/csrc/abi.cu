@@ -537,13 +537,50 @@ int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const in
                              plan, workspace, workspace_bytes, stream, nullptr, Extra());
 }
 
+size_t geot_b200_src_blocks_workspace_bytes(const geot_src_blocks_t *blocks, int64_t W, int dtype) {
+  if (!blocks) return 256;
+  size_t best = 256;
+  for (int b = 0; b < blocks->n_blocks; ++b)
+    best = std::max(best, geot_b200_workspace_bytes(blocks->bounds[b + 1] - blocks->bounds[b], W, dtype, 1));
+  return best;
+}
+
 int geot_b200_segment_reduce_ex(const void *src, const int64_t *src_index, const int64_t *dst_index,
                                 const void *weight, void *dst, int64_t E, int64_t S, int64_t H, int64_t F,
                                 int dtype, int reduce, int weight_layout, int sorted, const geot_plan_t *plan,
                                 void *workspace, size_t workspace_bytes, cudaStream_t stream,
                                 const geot_reduce_opts_t *opts) {
-  return segment_reduce_impl(src, src_index, dst_index, weight, dst, E, S, H, F, dtype, reduce, weight_layout, sorted,
-                             plan, workspace, workspace_bytes, stream, opts, Extra());
+  if (opts && opts->struct_size != sizeof(geot_reduce_opts_t)) return GEOT_ERR_INVALID_ARG;
+  if (!opts || !opts->src_blocks)
+    return segment_reduce_impl(src, src_index, dst_index, weight, dst, E, S, H, F, dtype, reduce, weight_layout, sorted,
+                               plan, workspace, workspace_bytes, stream, opts, Extra());
+  // src-blocked: one pass per block of the regrouped list; pass 0 writes every row of dst (unless the caller already
+  // accumulates), the others add their partial sums.  The caller's weights are read through the permutation.
+  const geot_src_blocks_t *bl = opts->src_blocks;
+  if (!src_index || bl->E != E || bl->n_blocks < 1 || bl->n_blocks > GEOT_MAX_SRC_BLOCKS || !sorted) return GEOT_ERR_INVALID_ARG;
+  if ((reduce != GEOT_SUM && reduce != GEOT_MEAN) || opts->edge_perm) return GEOT_ERR_UNSUPPORTED;
+  if (weight && weight_layout != GEOT_W_EDGE) return GEOT_ERR_UNSUPPORTED;
+  const int64_t *mean_rowptr = opts->mean_rowptr;
+  if (reduce == GEOT_MEAN && !mean_rowptr) {
+    if (!plan || !plan->rowptr || plan->S != S) return GEOT_ERR_INVALID_ARG;     // the degrees of the complete list
+    mean_rowptr = plan->rowptr;
+  }
+  bool first = true;
+  for (int b = 0; b < bl->n_blocks; ++b) {
+    const int64_t e0 = bl->bounds[b], n = bl->bounds[b + 1] - e0;
+    if (n <= 0) continue;
+    geot_reduce_opts_t o;
+    memset(&o, 0, sizeof(o));
+    o.struct_size = sizeof(o);
+    o.accumulate = (opts->accumulate || !first) ? 1 : 0;
+    o.edge_perm = weight ? bl->edge_perm + e0 : nullptr;
+    o.mean_rowptr = mean_rowptr;
+    const int rc = segment_reduce_impl(src, bl->src_index + e0, bl->dst_index + e0, weight, dst, n, S, H, F, dtype, reduce,
+                                       weight_layout, 1, nullptr, workspace, workspace_bytes, stream, &o, Extra());
+    if (rc != GEOT_OK) return rc;
+    first = false;
+  }
+  return GEOT_OK;
 }
 
 int geot_b200_index_scatter(const void *src, const int64_t *index, void *dst, int64_t E, int64_t S, int64_t F,

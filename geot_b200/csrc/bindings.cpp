@@ -19,6 +19,7 @@
 #include <torch/library.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <list>
 #include <mutex>
 #include <string>
@@ -91,13 +92,17 @@ geot_plan_t get_plan(const at::Tensor &dst_index, at::Tensor *keepalive) {
   const int dev = dst_index.get_device();
   {
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
-      if (it->storage_raw == raw && it->offset == off && it->numel == n && it->version == ver && it->device == dev &&
-          !it->storage.expired()) {
+    for (auto it = g_plans.begin(); it != g_plans.end();) {
+      if (it->storage.expired()) {          // the index tensor is gone: its plan can never hit again
+        it = g_plans.erase(it);
+        continue;
+      }
+      if (it->storage_raw == raw && it->offset == off && it->numel == n && it->version == ver && it->device == dev) {
         g_plans.splice(g_plans.begin(), g_plans, it);
         *keepalive = it->buf;
         return it->plan;
       }
+      ++it;
     }
   }
   auto stream = at::cuda::getCurrentCUDAStream();
@@ -125,11 +130,70 @@ geot_plan_t get_plan(const at::Tensor &dst_index, at::Tensor *keepalive) {
   return plan;
 }
 
+// ---- src-block cache (geot_b200_src_blocks_build: the graph regrouped by src-row block for the L2) ----------------
+// Keyed on both index tensors like the plan cache; an entry holds the regrouped list (20 bytes per edge).
+struct BlocksEntry {
+  c10::weak_intrusive_ptr<c10::StorageImpl> s_storage, d_storage;
+  const void *s_raw, *d_raw;
+  int64_t s_off, d_off, numel, n_src;
+  uint32_t s_ver, d_ver;
+  int device, n_blocks;
+  at::Tensor buf;
+  geot_src_blocks_t blocks;
+  BlocksEntry(c10::weak_intrusive_ptr<c10::StorageImpl> a, c10::weak_intrusive_ptr<c10::StorageImpl> b)
+      : s_storage(std::move(a)), d_storage(std::move(b)) {}
+};
+std::list<BlocksEntry> g_blocks;
+constexpr size_t kMaxBlocks = 4;
+
+geot_src_blocks_t get_src_blocks(const at::Tensor &src_index, const at::Tensor &dst_index, int64_t n_src, int n_blocks,
+                                 at::Tensor *keepalive) {
+  c10::StorageImpl *sr = src_index.storage().unsafeGetStorageImpl(), *dr = dst_index.storage().unsafeGetStorageImpl();
+  const int64_t so = src_index.storage_offset(), d_o = dst_index.storage_offset(), n = dst_index.numel();
+  const uint32_t sv = version_of(src_index), dv = version_of(dst_index);
+  const int dev = dst_index.get_device();
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto it = g_blocks.begin(); it != g_blocks.end();) {
+      if (it->s_storage.expired() || it->d_storage.expired()) {
+        it = g_blocks.erase(it);
+        continue;
+      }
+      if (it->s_raw == sr && it->d_raw == dr && it->s_off == so && it->d_off == d_o && it->numel == n && it->s_ver == sv &&
+          it->d_ver == dv && it->device == dev && it->n_blocks == n_blocks && it->n_src == n_src) {
+        g_blocks.splice(g_blocks.begin(), g_blocks, it);
+        *keepalive = it->buf;
+        return it->blocks;
+      }
+      ++it;
+    }
+  }
+  auto stream = at::cuda::getCurrentCUDAStream();
+  BlocksEntry e(src_index.storage().getWeakStorageImpl(), dst_index.storage().getWeakStorageImpl());
+  const size_t bytes = geot_b200_src_blocks_bytes(n), sbytes = geot_b200_src_blocks_scratch_bytes(n);
+  e.buf = at::empty({(int64_t)bytes}, dst_index.options().dtype(at::kByte));
+  at::Tensor scratch = at::empty({(int64_t)sbytes}, dst_index.options().dtype(at::kByte));
+  check_status(geot_b200_src_blocks_build(src_index.data_ptr<int64_t>(), dst_index.data_ptr<int64_t>(), n, n_src, n_blocks,
+                                          e.buf.data_ptr(), bytes, scratch.data_ptr(), sbytes, &e.blocks, stream),
+               "src_blocks_build");
+  e.s_raw = sr; e.d_raw = dr; e.s_off = so; e.d_off = d_o; e.numel = n; e.n_src = n_src;
+  e.s_ver = sv; e.d_ver = dv; e.device = dev; e.n_blocks = n_blocks;
+  *keepalive = e.buf;
+  geot_src_blocks_t blocks = e.blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    g_blocks.push_front(std::move(e));
+    while (g_blocks.size() > kMaxBlocks) g_blocks.pop_back();
+  }
+  return blocks;
+}
+
 void clear_csr_cache();
 void clear_plan_cache() {
   {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     g_plans.clear();
+    g_blocks.clear();
   }
   clear_csr_cache();
 }
@@ -189,12 +253,31 @@ at::Tensor run(const char *what, const at::Tensor &src_in, const c10::optional<a
   at::Tensor out = at::empty(out_shape, src.options());
   if (min_rows > S) out.narrow(0, S, min_rows - S).zero_();
   const int64_t W = H * F;
-  const size_t ws_bytes = geot_b200_workspace_bytes(E, W, dtype, sorted ? 1 : 0);
+  size_t ws_bytes = geot_b200_workspace_bytes(E, W, dtype, sorted ? 1 : 0);
+  // src-row blocking for the L2 (high-reuse graphs whose src matrix exceeds what the L2 keeps): the graph regrouped
+  // once, cached next to the plan.  GEOT_B200_SRC_BLOCKS: unset / 0 = the library's suggestion, 1 = off, n = n blocks.
+  geot_src_blocks_t blocks;
+  at::Tensor blocks_buf;
+  geot_reduce_opts_t opts;
+  memset(&opts, 0, sizeof(opts));
+  opts.struct_size = sizeof(opts);
+  const bool blockable = sorted && src_index.defined() && (reduce == GEOT_SUM || reduce == GEOT_MEAN) &&
+                         (weight_layout == GEOT_W_NONE || weight_layout == GEOT_W_EDGE);
+  if (blockable) {
+    const char *env = std::getenv("GEOT_B200_SRC_BLOCKS");
+    int nb = (env && env[0]) ? std::atoi(env) : 0;
+    if (nb <= 0) nb = geot_b200_src_blocks_suggest(E, S, src.size(0), W * (int64_t)src.element_size());
+    if (nb > 1 && nb <= GEOT_MAX_SRC_BLOCKS) {
+      blocks = get_src_blocks(src_index, dst_index, src.size(0), nb, &blocks_buf);
+      opts.src_blocks = &blocks;
+      ws_bytes = std::max(ws_bytes, geot_b200_src_blocks_workspace_bytes(&blocks, W, dtype));
+    }
+  }
   at::Tensor ws = at::empty({(int64_t)ws_bytes}, src.options().dtype(at::kByte));
-  const int st = geot_b200_segment_reduce(
+  const int st = geot_b200_segment_reduce_ex(
       src.data_ptr(), src_index.defined() ? src_index.data_ptr<int64_t>() : nullptr, dst_index.data_ptr<int64_t>(),
       weight.defined() ? weight.data_ptr() : nullptr, out.data_ptr(), E, S, H, F, dtype, reduce, weight_layout,
-      sorted ? 1 : 0, plan_ptr, ws.data_ptr(), ws_bytes, stream);
+      sorted ? 1 : 0, plan_ptr, ws.data_ptr(), ws_bytes, stream, opts.src_blocks ? &opts : nullptr);
   check_status(st, what);
   return out;
 }
@@ -326,12 +409,17 @@ at::Tensor csr_row_index(const at::Tensor &indptr, int64_t E) {
   const uint32_t ver = version_of(indptr);
   {
     std::lock_guard<std::mutex> lk(g_plan_mu);
-    for (auto it = g_csr.begin(); it != g_csr.end(); ++it) {
+    for (auto it = g_csr.begin(); it != g_csr.end();) {
+      if (it->storage.expired()) {          // the indptr tensor is gone: drop its [E] row index (8 bytes per edge)
+        it = g_csr.erase(it);
+        continue;
+      }
       if (it->storage_raw == raw && it->offset == indptr.storage_offset() && it->numel == indptr.numel() && it->E == E &&
-          it->version == ver && !it->storage.expired()) {
+          it->version == ver) {
         g_csr.splice(g_csr.begin(), g_csr, it);
         return it->row_index;
       }
+      ++it;
     }
   }
   at::Tensor row = at::empty({E}, indptr.options().dtype(at::kLong));
@@ -342,7 +430,7 @@ at::Tensor csr_row_index(const at::Tensor &indptr, int64_t E) {
   e.storage_raw = raw; e.offset = indptr.storage_offset(); e.numel = indptr.numel(); e.E = E; e.version = ver; e.row_index = row;
   std::lock_guard<std::mutex> lk(g_plan_mu);
   g_csr.push_front(std::move(e));
-  while (g_csr.size() > kMaxPlans) g_csr.pop_back();
+  while (g_csr.size() > 4) g_csr.pop_back();      // an entry holds 8 bytes per edge: keep few
   return row;
 }
 
@@ -360,6 +448,8 @@ at::Tensor csr_gws_impl(at::Tensor indptr, at::Tensor indices, at::Tensor weight
   TORCH_CHECK(src.dim() == 2, "src must be 2 dimensional");
   TORCH_CHECK(weight.dim() == 1 && weight.numel() == indices.numel(), "weight must be 1 dimensional with one entry per nonzero");
   TORCH_CHECK(indptr.scalar_type() == at::kLong || indptr.scalar_type() == at::kInt, "indptr must be int32 or int64");
+  TORCH_CHECK(indptr.is_cuda() && indptr.device() == src.device() && indices.is_cuda() && indices.device() == src.device(),
+              "geot::csr_gws: indptr, indices and src must be on the same CUDA device");
   c10::cuda::CUDAGuard guard(src.device());
   const at::Tensor ptr = indptr.contiguous();
   const int64_t E = indices.numel(), nrow = ptr.numel() - 1;

@@ -238,6 +238,32 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *gptr,
                : "memory");
 }
 
+// Rows [lo, hi) receive no edge: they read 0.  A cold path (the jump in dst_index is seen by one group), kept out of
+// line so that the close-a-row code of the main kernel stays small.
+template <typename T, int VECW, int LPR, int VPL>
+__device__ __noinline__ void fill_zero_rows(T *dst, int64_t W, int64_t lo, int64_t hi, int64_t col0, int gl) {
+  Vec<T, VECW> z;
+#pragma unroll
+  for (int i = 0; i < VECW; ++i) z.v[i] = from_acc<T>(typename AccOf<T>::type(0));
+#pragma unroll 1
+  for (int64_t r = lo; r < hi; ++r) {
+#pragma unroll 1
+    for (int j = 0; j < VPL; ++j) {
+      const int64_t c = col0 + (int64_t)(j * LPR + gl) * VECW;
+      if (c < W) *reinterpret_cast<Vec<T, VECW> *>(dst + r * W + c) = z;
+    }
+  }
+}
+
+// v / n for an integer count n, n_inv = RN(1 / n): one multiply and two FMAs (Markstein's correction step: the residual
+// v - q*n is exact in an FMA) instead of a division sequence per element -- equal to IEEE division on every tested
+// input (tests/test_abi_host.py::test_mean_division_identity), and 10x fewer instructions at every store site.
+template <typename A> __device__ __forceinline__ A div_by_count(A v, A n, A n_inv) {
+  const A q = v * n_inv;
+  const A r = fma(-q, n, v);
+  return fma(r, n_inv, q);
+}
+
 template <typename T, int VECW, int LPR, int VPL, int RED, int WM, int PF_>
 __global__ void __launch_bounds__(kThreads, (ShapeOf<T, VECW, LPR, VPL, PF_>::min_blocks))
 segment_reduce_kernel(const Params p) {
@@ -349,7 +375,12 @@ segment_reduce_kernel(const Params p) {
   };
 
   auto finalize_store = [&](int64_t row, A(&a)[VPL][VECW], long long n) {
-    if (p.mean && p.mean_rowptr != nullptr) n = p.mean_rowptr[row + 1] - p.mean_rowptr[row];
+    A nA = A(1), n_inv = A(1);
+    if (p.mean) {
+      if (p.mean_rowptr != nullptr) n = p.mean_rowptr[row + 1] - p.mean_rowptr[row];
+      nA = static_cast<A>(n);
+      n_inv = A(1) / nA;
+    }
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       if (!col_ok[j]) continue;
@@ -359,24 +390,15 @@ segment_reduce_kernel(const Params p) {
 #pragma unroll
       for (int i = 0; i < VECW; ++i) {
         A v = a[j][i];
-        if (p.mean) v = v / static_cast<A>(n);
+        if (p.mean) v = div_by_count<A>(v, nA, n_inv);
         if (p.accumulate) v = to_acc<T>(out.v[i]) + v;
         out.v[i] = from_acc<T>(v);
       }
       *q = out;
     }
   };
-  // rows [lo, hi) receive no edge: they read 0 (zero_gaps; a cold path -- the jump in dst_index is seen by one group)
-  auto fill_gap = [&](int64_t lo, int64_t hi) {
-    VecT z;
-#pragma unroll
-    for (int i = 0; i < VECW; ++i) z.v[i] = from_acc<T>(A(0));
-    for (int64_t r = lo; r < hi; ++r) {
-#pragma unroll
-      for (int j = 0; j < VPL; ++j)
-        if (col_ok[j]) *reinterpret_cast<VecT *>(dst + r * W + col[j]) = z;
-    }
-  };
+  // rows [lo, hi) receive no edge (zero_gaps)
+  auto fill_gap = [&](int64_t lo, int64_t hi) { fill_zero_rows<T, VECW, LPR, VPL>(dst, W, lo, hi, col0, gl); };
 
   if (e_begin < e_end) {
     const int64_t prev_row = (e_begin > 0) ? dst_index[e_begin - 1] : -1;
@@ -390,7 +412,7 @@ segment_reduce_kernel(const Params p) {
 
     // closes the open run, whose row is `row`; the run that starts has row `next`
     auto close_run = [&](int64_t row, int64_t next) {
-      if (p.zero_gaps && next > row + 1) fill_gap(row + 1, next);
+      if (next > row + 1) fill_gap(row + 1, next);         // (callers pass next = row + 1 unless zero_gaps)
       if (is_head) {
         park(s_head + g * CW, s_head_cnt, s_head_row, row);
         flags |= FLAG_HEAD;
@@ -526,9 +548,10 @@ segment_reduce_kernel(const Params p) {
                 if ((sub >> u) & 1u) {
                   const int kb = k - batch_pos;           // position inside the batch
                   const uint32_t row = __shfl_sync(gmask, d_cur, kb > 0 ? kb - 1 : 0, LPR);
-                  const uint32_t nxt = __shfl_sync(gmask, d_cur, kb, LPR);
+                  const int64_t prev = (int64_t)(kb > 0 ? row : batch_left);
+                  const int64_t nxt = p.zero_gaps ? (int64_t)__shfl_sync(gmask, d_cur, kb, LPR) : prev + 1;
                   cnt = k - run_start;
-                  close_run((int64_t)(kb > 0 ? row : batch_left), (int64_t)nxt);
+                  close_run(prev, nxt);
                   run_start = k;
                 }
                 VecT vv[VPL];
@@ -564,7 +587,7 @@ segment_reduce_kernel(const Params p) {
         VecT v[VPL];
 #pragma unroll
         for (int j = 0; j < VPL; ++j) v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + sid * row_bytes);
-        if (d != ld32) close_run((int64_t)ld32, (int64_t)d);
+        if (d != ld32) close_run((int64_t)ld32, p.zero_gaps ? (int64_t)d : (int64_t)ld32 + 1);
         add_edge(v, we);
         ++cnt;
         ld32 = d;
@@ -700,7 +723,7 @@ segment_reduce_kernel(const Params p) {
                 if ((sub >> u) & 1u) {
                   const int k = k0 + u;
                   const int64_t row = (k == 0) ? batch_left : __shfl_sync(gmask, my_dst, (k == 0) ? 0 : k - 1, LPR);
-                  close_run(row, __shfl_sync(gmask, my_dst, k, LPR));
+                  close_run(row, p.zero_gaps ? __shfl_sync(gmask, my_dst, k, LPR) : row + 1);
                 }
                 accumulate(v[u], w[u]);
                 ++cnt;
@@ -721,7 +744,10 @@ segment_reduce_kernel(const Params p) {
               w[j] = we;
               if (WM == WM_GENERIC && wb[j] != nullptr) w[j] = to_acc<T>(__ldg(wb[j] + k * ws_e32));
             }
-            if ((bmask >> k) & 1u) close_run(k == 0 ? batch_left : row, __shfl_sync(gmask, my_dst, k, LPR));
+            if ((bmask >> k) & 1u) {
+              const int64_t prev = (k == 0) ? batch_left : row;
+              close_run(prev, p.zero_gaps ? __shfl_sync(gmask, my_dst, k, LPR) : prev + 1);
+            }
             accumulate(v, w);
             ++cnt;
           }
@@ -787,12 +813,15 @@ segment_reduce_kernel(const Params p) {
     }
   };
 
-  if (g == 0 && (flags & FLAG_HEAD)) {
-    // chain that entered the tile from the left; it continues while chunks are THROUGH
-    if (flags & FLAG_THROUGH) run_chain(s_head, s_head_cnt[0], s_head_row[0], 1, true);
-    else run_chain(s_head, s_head_cnt[0], s_head_row[0], NG, true);
+  // a group may own two chains: the one that entered the tile from the left (chunk 0 only; it continues while chunks
+  // are THROUGH) and the one its own tail partial starts.  One call site, so that the chain code exists once.
+  const bool own_head = (g == 0) && (flags & FLAG_HEAD);
+  const bool own_tail = (flags & FLAG_TAIL) != 0;
+  for (int which = own_head ? 0 : 1; which < (own_tail ? 2 : 1); ++which) {
+    const bool h = (which == 0);
+    run_chain(h ? s_head : tail_slot(g), h ? s_head_cnt[0] : s_tail_cnt[g], h ? s_head_row[0] : s_tail_row[g],
+              h ? ((flags & FLAG_THROUGH) ? 1 : NG) : g + 1, h);
   }
-  if (flags & FLAG_TAIL) run_chain(tail_slot(g), s_tail_cnt[g], s_tail_row[g], g + 1, false);
 
   // tile-level flags follow from the index alone
   if (tid == 0 && first_col_tile) {

@@ -135,12 +135,15 @@ GEOT_API int geot_b200_segment_reduce(const void *src, const int64_t *src_index,
  *                caller's weight order).  GEOT_W_EDGE weights, sorted input, sum / mean only.
  *   mean_rowptr  [S+1] int64, device: reduce == GEOT_MEAN divides by mean_rowptr[r+1] - mean_rowptr[r] (the row's
  *                degree in the complete edge list) instead of by this pass's own count, so partial means add up. */
+typedef struct geot_src_blocks geot_src_blocks_t;
 typedef struct geot_reduce_opts {
   size_t struct_size;
   int32_t accumulate;
   int32_t reserved;
   const int32_t *edge_perm;
   const int64_t *mean_rowptr;
+  const geot_src_blocks_t *src_blocks;  /* the graph regrouped by src-row block (below): the call reduces block
+                                           after block; src_index / dst_index must be the arrays it was built from */
 } geot_reduce_opts_t;
 
 GEOT_API int geot_b200_segment_reduce_ex(const void *src, const int64_t *src_index, const int64_t *dst_index,
@@ -148,6 +151,35 @@ GEOT_API int geot_b200_segment_reduce_ex(const void *src, const int64_t *src_ind
                                 int64_t F, int dtype, int reduce, int weight_layout, int sorted,
                                 const geot_plan_t *plan, void *workspace, size_t workspace_bytes,
                                 cudaStream_t stream, const geot_reduce_opts_t *opts);
+
+/* ---- src-row blocking for the L2 (format_preprocess family; once per graph) ------------------------------------
+ * A gather op re-reads src rows E / N_src times; a src matrix beyond what the L2 keeps of a read-shared working set
+ * (~60 MB measured on B200) turns those re-reads into DRAM traffic (Reddit-shape F=128: 17 GB per call instead of
+ * 2.5).  The edge list is regrouped once, stably, by src-row block; every block is still dst-sorted, and
+ * geot_b200_segment_reduce_ex (opts.src_blocks) reduces block after block, the later ones accumulating into dst.
+ * Results equal the one-pass results within the sum tolerance (the summation order inside a row changes); sum / mean
+ * with at most one weight per edge.
+ *   suggest   number of blocks worth using for this shape (1: do not block)
+ *   bytes / scratch_bytes   device buffer that holds the regrouped list / scratch for building it (256-byte aligned)
+ *   build     fills buf and *blocks; synchronises `stream` once. */
+#define GEOT_MAX_SRC_BLOCKS 16
+struct geot_src_blocks {
+  int64_t E;
+  int32_t n_blocks;
+  int32_t reserved;
+  int64_t bounds[GEOT_MAX_SRC_BLOCKS + 1];  /* edge offsets of the blocks in the arrays below */
+  const int64_t *dst_index;                 /* [E] device: the regrouped list */
+  const int64_t *src_index;                 /* [E] */
+  const int32_t *edge_perm;                 /* [E]: position of regrouped edge e in the caller's list (weights) */
+};
+GEOT_API int geot_b200_src_blocks_suggest(int64_t E, int64_t S, int64_t N_src, int64_t row_bytes);
+GEOT_API size_t geot_b200_src_blocks_bytes(int64_t E);
+GEOT_API size_t geot_b200_src_blocks_scratch_bytes(int64_t E);
+GEOT_API int geot_b200_src_blocks_build(const int64_t *src_index, const int64_t *dst_index, int64_t E, int64_t N_src,
+                               int n_blocks, void *buf, size_t buf_bytes, void *scratch, size_t scratch_bytes,
+                               geot_src_blocks_t *blocks, cudaStream_t stream);
+/* Scratch for geot_b200_segment_reduce_ex with opts.src_blocks (every block partitions on its own). */
+GEOT_API size_t geot_b200_src_blocks_workspace_bytes(const geot_src_blocks_t *blocks, int64_t W, int dtype);
 
 /* Replaces index_scatter_cuda (header_cuda.h:4-6; csrc/cuda/index_scatter_cuda.cu:86-105), dim = 0:
  * src viewed as [E, F] (wrapper/index_scatter_base.h:15-17).  sorted == 0 takes the atomic kernel

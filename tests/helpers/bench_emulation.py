@@ -57,7 +57,7 @@ def install(rank=0, world=1):
             self.nbytes = 0
 
     def segment_reduce(src, si, di, w, reduce="sum", *, S=None, H=1, weight_layout=None, sorted=True, plan=None, out=None,
-                       workspace=None, accumulate=False, edge_perm=None, mean_rowptr=None):
+                       workspace=None, accumulate=False, edge_perm=None, mean_rowptr=None, src_blocks=None):
         if w is not None and edge_perm is not None:
             w = w[edge_perm.long()]
         red = "sum" if mean_rowptr is not None else reduce
@@ -99,6 +99,7 @@ def install(rank=0, world=1):
     abi.segment_reduce_host = (lambda src, si, di, w, reduce="sum", *, S, H=1, weight_layout=None, out=None:
                                segment_reduce(src, si, di, w, reduce, S=S, H=H, out=out))
     abi.permute_edges = permute
+    abi.src_blocks_suggest = lambda *a: 1
     abi.profile_enable = lambda n: calls.__setitem__("n", n)
     abi.profile_read = lambda cap=4096: [0.05] * min(cap, max(calls["n"], 1))
     abi.host_last_transfer = lambda: (1000, 10)

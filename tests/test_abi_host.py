@@ -218,3 +218,52 @@ def test_reference_side_binding_compiles(tmp_path):
            + ["-I" + p for p in include_paths()])
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_reference_import_name_resolves():
+    """`import geot` (the reference's package name, /root/reference/geot/__init__.py:4-9) is served by geot_b200."""
+    import geot
+    import geot_b200
+    for name in ("index_scatter", "gather_scatter", "gather_weight_scatter", "mh_spmm", "mh_spmm_transposed", "csr_gws", "coo_to_csr"):
+        assert getattr(geot, name) is getattr(geot_b200, name), name
+    from geot.match_replace import pattern_transform
+    assert pattern_transform is geot_b200.pattern_transform
+
+
+def test_mean_division_identity():
+    """The kernels divide by the segment length with one multiply and two FMAs (segment_reduce.cuh div_by_count:
+    q = v * RN(1/n); q' = fma(fma(-q, n, v), RN(1/n), q)) instead of a division per element.  Restated in numpy
+    (fp32 FMA emulated through fp64: products of two fp32 values are exact there) it must equal IEEE fp32 division for
+    integer n, including the n = 2^k - 1 significands where the plain reciprocal multiply is off by one ulp."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+
+    def fma32(a, b, c):
+        return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+    ns = np.concatenate([np.arange(1, 5000), 2 ** np.arange(1, 24) - 1, rng.integers(1, 300000, 20000)]).astype(np.float32)
+    plain_bad = 0
+    for trial in range(6):
+        if trial == 0:
+            a = ns.copy()                                        # mean of ones
+        elif trial == 1:
+            a = (ns * np.float32(3.0)).astype(np.float32)
+        else:
+            a = (rng.random(ns.size).astype(np.float32) * ns * np.float32(1.7)).astype(np.float32)
+        inv = (np.float32(1.0) / ns).astype(np.float32)
+        q = (a * inv).astype(np.float32)
+        got = fma32(fma32(-q, ns, a), inv, q)
+        assert np.array_equal(got, (a / ns).astype(np.float32)), trial
+        plain_bad += int((q != (a / ns).astype(np.float32)).sum())
+    assert plain_bad > 0          # (the correction step is needed: the plain product is not always the quotient)
+
+
+def test_src_blocks_suggestion_rule():
+    """geot_b200_src_blocks_suggest (pure host arithmetic): high-reuse graphs whose src matrix exceeds what the L2 keeps
+    are blocked, resident or low-reuse ones are not (profiles/r02a_blocks.txt, r02a_l2probe.txt)."""
+    from geot_b200 import abi
+    assert abi.src_blocks_suggest(114_615_892, 232_965, 232_965, 512) == 2        # Reddit shape, F = 128 fp32: 119 MB
+    assert abi.src_blocks_suggest(39_561_252, 132_534, 132_534, 1024) == 2        # proteins shape, F = 256: 136 MB
+    assert abi.src_blocks_suggest(114_615_892, 232_965, 232_965, 256) == 1        # 60 MB: already resident
+    assert abi.src_blocks_suggest(61_859_140, 2_449_029, 2_449_029, 256) == 1     # products: degree 25, no reuse to save
+    assert abi.src_blocks_suggest(1_166_243, 169_343, 169_343, 512) == 1          # arxiv
+    assert abi.src_blocks_suggest(0, 1, 1, 4) == 1

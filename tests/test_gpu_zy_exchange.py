@@ -225,7 +225,7 @@ def test_resident_host_graph_matches_stateless_host_entry():
         assert h2d == x.numel() * 4 + E * 4 and d2h == S * F * 4 and resident == 2 * E * 8
     assert torch.equal(hg.reduce(x, None, "max"), oracle.segment_reduce(x, si, di, None, "max", S=S))
     got = hg.reduce(x, None, "mean")
-    assert torch.allclose(got, oracle.segment_reduce(x, si, di, None, "mean", S=S), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got, oracle.segment_reduce(x, si, di, None, "mean", S=S, acc64=True), rtol=1e-5, atol=1e-6)
     wh = torch.rand(E, 4, generator=g).bfloat16()
     xh = torch.rand(N, 4, 16, generator=g).bfloat16()
     got = hg.reduce(xh, wh, "sum", H=4)
@@ -235,3 +235,78 @@ def test_resident_host_graph_matches_stateless_host_entry():
     got = hi.reduce(xe, None, "sum")
     assert torch.allclose(got, oracle.segment_reduce(xe, None, di, None, "sum", S=S, acc64=True), rtol=1e-5, atol=1e-6)
     hi.close()
+
+
+@pytest.mark.parametrize("n_blocks", [2, 3, 16])
+@pytest.mark.parametrize("dtype,F", [(torch.float32, 128), (torch.float32, 20), (torch.bfloat16, 64)])
+def test_src_blocked_reduction(monkeypatch, n_blocks, dtype, F):
+    """geot_b200_src_blocks_build + segment_reduce_ex(opts.src_blocks): the edge list regrouped stably by src-row
+    block (every block dst-sorted, a permutation of the caller's list), reduced block after block into one output.
+    Equal to the one-pass result within the sum tolerance; the torch operators take the same path under
+    GEOT_B200_SRC_BLOCKS=n and stay within tolerance of the oracle."""
+    import oracle
+    import geot_b200
+    g = torch.Generator().manual_seed(n_blocks * 100 + F)
+    N, E = 1500, 120000
+    wdeg = torch.rand(N, generator=g) ** 4
+    wdeg[N // 2] = 0.3 * float(wdeg.sum())
+    wdeg[7:19] = 0
+    di_c = torch.multinomial(wdeg / wdeg.sum(), E, replacement=True, generator=g).sort().values
+    si_c = torch.randint(0, N, (E,), generator=g)
+    key = di_c * N + si_c                                          # (dst, src)-sorted like the benchmark graphs
+    key = key.sort().values
+    di_c, si_c = key // N, key % N
+    w_c = (torch.rand(E, generator=g) + 0.25).to(dtype)
+    x_c = (torch.rand(N, F, generator=g) + 0.5).to(dtype)
+    S = N
+    di, si, w, x = di_c.to(DEV), si_c.to(DEV), w_c.to(DEV), x_c.to(DEV)
+    bl = abi.SrcBlocks(si, di, N, n_blocks)
+    assert bl.bounds[0] == 0 and bl.bounds[-1] == E and all(bl.bounds[i] <= bl.bounds[i + 1] for i in range(n_blocks))
+    perm = bl.edge_perm.cpu().long()
+    assert torch.equal(perm.sort().values, torch.arange(E))
+    assert torch.equal(bl.src_index.cpu(), si_c[perm]) and torch.equal(bl.dst_index.cpu(), di_c[perm])
+    per = (N + n_blocks - 1) // n_blocks
+    for b in range(n_blocks):
+        s_b, d_b = bl.src_index[bl.bounds[b]:bl.bounds[b + 1]].cpu(), bl.dst_index[bl.bounds[b]:bl.bounds[b + 1]].cpu()
+        assert bool(((s_b >= b * per) & (s_b < (b + 1) * per)).all()) and bool((d_b[1:] >= d_b[:-1]).all())
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    plan = abi.DevicePlan(di, S)
+    for reduce in ("sum", "mean"):
+        for ww, wc in ((None, None), (w, w_c)):
+            out = torch.full((S, F), 5.0, dtype=dtype, device=DEV)
+            abi.segment_reduce(x, si, di, ww, reduce, S=S, plan=plan, out=out, src_blocks=bl)
+            exp = oracle.segment_reduce(x_c, si_c, di_c, wc, reduce, S=S, acc64=(dtype == torch.float32))
+            assert torch.allclose(out.cpu().double(), exp.double(), rtol=tol, atol=1e-6), (reduce, ww is None)
+    with pytest.raises(abi.AbiError):
+        abi.segment_reduce(x, si, di, None, "max", S=S, plan=plan, src_blocks=bl)
+    # the torch operators under a forced block count
+    monkeypatch.setenv("GEOT_B200_SRC_BLOCKS", str(n_blocks))
+    geot_b200.clear_plan_cache()
+    got = geot_b200.gather_weight_scatter(si, di, w, x)
+    exp = oracle.gather_weight_scatter(si_c, di_c, w_c, x_c, acc64=(dtype == torch.float32))
+    assert torch.allclose(got.cpu().double(), exp.double(), rtol=tol, atol=1e-6)
+    got2 = geot_b200.gather_weight_scatter(si, di, w, x)           # cached regrouped list: bit-identical
+    assert torch.equal(got, got2)
+    got = geot_b200.gather_scatter(si, di, x, "mean")
+    assert torch.allclose(got.cpu().double(), oracle.gather_scatter(si_c, di_c, x_c, "mean", acc64=(dtype == torch.float32)).double(),
+                          rtol=tol, atol=1e-6)
+    assert torch.equal(geot_b200.gather_scatter(si, di, x, "max").cpu(), oracle.gather_scatter(si_c, di_c, x_c, "max"))   # not blocked
+    geot_b200.clear_plan_cache()
+
+
+def test_mean_of_constant_rows_is_the_constant_exactly():
+    """mean divides by the segment length through a reciprocal + correction step (div_by_count): when every src row
+    holds the same dyadic constants the sums n*c are exact and the mean must return c bit for bit, for every degree
+    of the graph (1 .. hub), in-kernel rows and rows finished by the fixup pass alike."""
+    import geot_b200
+    g = torch.Generator().manual_seed(3)
+    N, E, F = 4000, 300000, 32
+    wdeg = torch.rand(N, generator=g) ** 6
+    wdeg[11] = 0.2 * float(wdeg.sum())
+    di = torch.multinomial(wdeg / wdeg.sum(), E, replacement=True, generator=g).sort().values
+    di = torch.cat([di, torch.arange(N)]).sort().values           # every row non-empty, many of degree 1
+    si = torch.randint(0, N, (di.numel(),), generator=g)
+    c = (torch.randint(64, 128, (F,), generator=g).float() / 64.0)  # in [1, 2), 6 fractional bits: n*c exact for n < 2^17
+    x = c.unsqueeze(0).expand(N, F).contiguous()
+    got = geot_b200.gather_scatter(si.to(DEV), di.to(DEV), x.to(DEV), "mean").cpu()
+    assert torch.equal(got, x)

@@ -319,7 +319,7 @@ class Runner:
             nb = int(os.environ.get("GEOT_B200_SRC_BLOCKS", "0"))
             if self.gather and H == 1 and self.exchange in ("none", "replicated"):
                 if nb <= 0:
-                    nb = abi.src_blocks_suggest(self.E, self.S, wk["N"], self.W * wk["esize"])
+                    nb = abi.src_blocks_suggest(self.E, self.S, wk["N"], self.W * wk["esize"]) if wk["esize"] >= 4 else 1
                 if nb > 1:
                     self.blocks = abi.SrcBlocks(self.si, self.di, wk["N"], nb)
             self.ws = abi.Workspace(self.E, self.W, wk["dtype"], dev, src_blocks=self.blocks)

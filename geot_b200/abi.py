@@ -60,7 +60,7 @@ _lib = None
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        path = os.environ.get("GEOT_B200_LIB", LIB_PATH)   # tuning builds (Makefile VARIANT=...)
+        path = os.environ.get("GEOT_B200_LIB") or LIB_PATH   # tuning builds (Makefile VARIANT=...)
         if not os.path.exists(path):
             raise ImportError("geot_b200: %s not built; there is no fallback" % path)
         L = ctypes.CDLL(path)

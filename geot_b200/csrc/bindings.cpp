@@ -266,7 +266,8 @@ at::Tensor run(const char *what, const at::Tensor &src_in, const c10::optional<a
   if (blockable) {
     const char *env = std::getenv("GEOT_B200_SRC_BLOCKS");
     int nb = (env && env[0]) ? std::atoi(env) : 0;
-    if (nb <= 0) nb = geot_b200_src_blocks_suggest(E, S, src.size(0), W * (int64_t)src.element_size());
+    // (automatic only for 4- / 8-byte elements: a 16-bit output would be rounded once per pass)
+    if (nb <= 0) nb = src.element_size() >= 4 ? geot_b200_src_blocks_suggest(E, S, src.size(0), W * (int64_t)src.element_size()) : 1;
     if (nb > 1 && nb <= GEOT_MAX_SRC_BLOCKS) {
       blocks = get_src_blocks(src_index, dst_index, src.size(0), nb, &blocks_buf);
       opts.src_blocks = &blocks;

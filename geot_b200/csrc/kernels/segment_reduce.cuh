@@ -267,6 +267,16 @@ template <typename A> __device__ __forceinline__ A div_by_count(A v, A n, A n_in
 template <typename T, int VECW, int LPR, int VPL, int RED, int WM, int PF_>
 __global__ void __launch_bounds__(kThreads, (ShapeOf<T, VECW, LPR, VPL, PF_>::min_blocks))
 segment_reduce_kernel(const Params p) {
+  // the options of geot_b200_segment_reduce_ex (GEOT_NO_EXT: a tuning build without them, to measure what they cost)
+#ifdef GEOT_NO_EXT
+  constexpr bool kExt = false;
+#else
+  constexpr bool kExt = true;
+#endif
+  const bool o_accumulate = kExt && p.accumulate != 0;
+  const bool o_zero_gaps = kExt && p.zero_gaps != 0;
+  const int64_t *const o_mean_rowptr = kExt ? p.mean_rowptr : nullptr;
+  const int32_t *const o_edge_perm = kExt ? p.edge_perm : nullptr;
   using A = typename AccOf<T>::type;
   using VecT = Vec<T, VECW>;
   using SH = ShapeOf<T, VECW, LPR, VPL, PF_>;
@@ -377,7 +387,7 @@ segment_reduce_kernel(const Params p) {
   auto finalize_store = [&](int64_t row, A(&a)[VPL][VECW], long long n) {
     A nA = A(1), n_inv = A(1);
     if (p.mean) {
-      if (p.mean_rowptr != nullptr) n = p.mean_rowptr[row + 1] - p.mean_rowptr[row];
+      if (o_mean_rowptr != nullptr) n = o_mean_rowptr[row + 1] - o_mean_rowptr[row];
       nA = static_cast<A>(n);
       n_inv = A(1) / nA;
     }
@@ -386,12 +396,12 @@ segment_reduce_kernel(const Params p) {
       if (!col_ok[j]) continue;
       VecT *q = reinterpret_cast<VecT *>(dst + row * W + col[j]);
       VecT out;
-      if (p.accumulate) out = *q;
+      if (o_accumulate) out = *q;
 #pragma unroll
       for (int i = 0; i < VECW; ++i) {
         A v = a[j][i];
         if (p.mean) v = div_by_count<A>(v, nA, n_inv);
-        if (p.accumulate) v = to_acc<T>(out.v[i]) + v;
+        if (o_accumulate) v = to_acc<T>(out.v[i]) + v;
         out.v[i] = from_acc<T>(v);
       }
       *q = out;
@@ -405,7 +415,7 @@ segment_reduce_kernel(const Params p) {
     const int64_t next_row = (e_end < E) ? dst_index[e_end] : -1;
     int64_t last_dst = dst_index[e_begin];   // dst of the edge left of the current batch
     bool is_head = (last_dst == prev_row);   // the open run entered the chunk from the left
-    if (p.zero_gaps) {
+    if (o_zero_gaps) {
       const int64_t left_row = (e_begin > 0) ? prev_row : p.fill_lo - 1;
       if (last_dst > left_row + 1) fill_gap(left_row + 1, last_dst);
     }
@@ -456,7 +466,7 @@ segment_reduce_kernel(const Params p) {
         d = (uint32_t)ld_stream(dst_index + e, pol);
         sid = src_index ? (uint32_t)ld_stream(src_index + e, pol) : (uint32_t)e;
         wv = 1.f;
-        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + (p.edge_perm ? (int64_t)ld_stream32(p.edge_perm + e, pol) : e), pol));
+        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + (o_edge_perm ? (int64_t)ld_stream32(o_edge_perm + e, pol) : e), pol));
       };
       // copies the U rows whose ids are at o[0..U) into ring stage st (compile-time)
       auto issue = [&](const uint32_t *o, int st) {
@@ -549,7 +559,7 @@ segment_reduce_kernel(const Params p) {
                   const int kb = k - batch_pos;           // position inside the batch
                   const uint32_t row = __shfl_sync(gmask, d_cur, kb > 0 ? kb - 1 : 0, LPR);
                   const int64_t prev = (int64_t)(kb > 0 ? row : batch_left);
-                  const int64_t nxt = p.zero_gaps ? (int64_t)__shfl_sync(gmask, d_cur, kb, LPR) : prev + 1;
+                  const int64_t nxt = o_zero_gaps ? (int64_t)__shfl_sync(gmask, d_cur, kb, LPR) : prev + 1;
                   cnt = k - run_start;
                   close_run(prev, nxt);
                   run_start = k;
@@ -583,11 +593,11 @@ segment_reduce_kernel(const Params p) {
         const uint32_t d = (uint32_t)dst_index[e];
         const int64_t sid = src_index ? src_index[e] : e;
         float we = 1.f;
-        if (WM == WM_EDGE) we = to_acc<T>(weight[p.edge_perm ? (int64_t)p.edge_perm[e] : e]);
+        if (WM == WM_EDGE) we = to_acc<T>(weight[o_edge_perm ? (int64_t)o_edge_perm[e] : e]);
         VecT v[VPL];
 #pragma unroll
         for (int j = 0; j < VPL; ++j) v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + sid * row_bytes);
-        if (d != ld32) close_run((int64_t)ld32, p.zero_gaps ? (int64_t)d : (int64_t)ld32 + 1);
+        if (d != ld32) close_run((int64_t)ld32, o_zero_gaps ? (int64_t)d : (int64_t)ld32 + 1);
         add_edge(v, we);
         ++cnt;
         ld32 = d;
@@ -602,7 +612,7 @@ segment_reduce_kernel(const Params p) {
         const int64_t s = valid ? (src_index ? ld_stream(src_index + my_e, pol) : my_e) : 0;
         my_off = s * row_bytes;
         my_w = A(1);
-        if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + (p.edge_perm ? (int64_t)ld_stream32(p.edge_perm + my_e, pol) : my_e), pol));
+        if (WM == WM_EDGE && valid) my_w = to_acc<T>(ld_stream_t<T>(weight + (o_edge_perm ? (int64_t)ld_stream32(o_edge_perm + my_e, pol) : my_e), pol));
       };
 
       // operands of the current batch (my_*) and of the next one (n_*); the one after that is loaded at the
@@ -723,7 +733,7 @@ segment_reduce_kernel(const Params p) {
                 if ((sub >> u) & 1u) {
                   const int k = k0 + u;
                   const int64_t row = (k == 0) ? batch_left : __shfl_sync(gmask, my_dst, (k == 0) ? 0 : k - 1, LPR);
-                  close_run(row, p.zero_gaps ? __shfl_sync(gmask, my_dst, k, LPR) : row + 1);
+                  close_run(row, o_zero_gaps ? __shfl_sync(gmask, my_dst, k, LPR) : row + 1);
                 }
                 accumulate(v[u], w[u]);
                 ++cnt;
@@ -746,7 +756,7 @@ segment_reduce_kernel(const Params p) {
             }
             if ((bmask >> k) & 1u) {
               const int64_t prev = (k == 0) ? batch_left : row;
-              close_run(prev, p.zero_gaps ? __shfl_sync(gmask, my_dst, k, LPR) : prev + 1);
+              close_run(prev, o_zero_gaps ? __shfl_sync(gmask, my_dst, k, LPR) : prev + 1);
             }
             accumulate(v, w);
             ++cnt;
@@ -759,7 +769,7 @@ segment_reduce_kernel(const Params p) {
 
     // the run still open at the chunk end
     const int64_t cur_row = last_dst;
-    if (p.zero_gaps && e_end == E && p.fill_hi > cur_row + 1) fill_gap(cur_row + 1, p.fill_hi);
+    if (o_zero_gaps && e_end == E && p.fill_hi > cur_row + 1) fill_gap(cur_row + 1, p.fill_hi);
     const bool continues = (cur_row == next_row);
     if (is_head) {                      // the whole chunk is one run that entered from the left
       park(s_head + g * CW, s_head_cnt, s_head_row, cur_row);

@@ -330,11 +330,27 @@ class BucketedGather:
         if k not in self._plans:
             self._plans[k] = abi.DevicePlan(di, S)
         W = x[0].numel()
-        key = (k, W, x.dtype)                              # scratch is sized per (bucket, row width, dtype)
-        if key not in self._ws:
-            self._ws[key] = abi.Workspace(e1 - e0, W, x.dtype, x.device)
         H = x.shape[1] if x.dim() == 3 else 1
-        abi.segment_reduce(x, si, di, weight, reduce, S=S, H=H, plan=self._plans[k], out=out, workspace=self._ws[key],
+        key = (k, W, x.dtype)                              # scratch / blocking are per (bucket, row width, dtype)
+        if key not in self._ws:
+            # src-row blocking for the L2 inside the bucket (the remote bucket of a Reddit-shape shard gathers from the
+            # whole replica: same reuse, same working set as on one GPU).  The regrouped list carries its own
+            # permutation; composed with the bucket's, it indexes the caller's weights directly.
+            blocks = None
+            nb = 1
+            if H == 1 and self.cuda and x.element_size() >= 4:         # (16-bit outputs would be rounded once per pass)
+                nb = abi.src_blocks_suggest(e1 - e0, S, x.shape[0], W * x.element_size())
+            if nb > 1:
+                blocks = abi.SrcBlocks(si, di, x.shape[0], nb)
+                blocks.composed_perm = perm[blocks.edge_perm.long()].contiguous()
+                blocks.c.edge_perm = blocks.composed_perm.data_ptr()
+            self._ws[key] = (abi.Workspace(e1 - e0, W, x.dtype, x.device, src_blocks=blocks), blocks)
+        ws, blocks = self._ws[key]
+        if blocks is not None:
+            abi.segment_reduce(x, si, di, weight, reduce, S=S, H=H, plan=self._plans[k], out=out, workspace=ws,
+                               accumulate=accumulate, mean_rowptr=mean_rowptr, src_blocks=blocks)
+            return
+        abi.segment_reduce(x, si, di, weight, reduce, S=S, H=H, plan=self._plans[k], out=out, workspace=ws,
                            accumulate=accumulate, edge_perm=perm if weight is not None else None, mean_rowptr=mean_rowptr)
 
     def _bucket_order(self, weight):

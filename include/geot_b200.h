@@ -158,7 +158,9 @@ GEOT_API int geot_b200_segment_reduce_ex(const void *src, const int64_t *src_ind
  * 2.5).  The edge list is regrouped once, stably, by src-row block; every block is still dst-sorted, and
  * geot_b200_segment_reduce_ex (opts.src_blocks) reduces block after block, the later ones accumulating into dst.
  * Results equal the one-pass results within the sum tolerance (the summation order inside a row changes); sum / mean
- * with at most one weight per edge.
+ * with at most one weight per edge.  The passes accumulate INTO dst, so a bf16 / fp16 dst is rounded once per pass:
+ * callers that hold the 1e-2 bound of 16-bit types keep the block count small (the torch bindings block fp32 / fp64
+ * automatically and 16-bit types only on request).
  *   suggest   number of blocks worth using for this shape (1: do not block)
  *   bytes / scratch_bytes   device buffer that holds the regrouped list / scratch for building it (256-byte aligned)
  *   build     fills buf and *blocks; synchronises `stream` once. */

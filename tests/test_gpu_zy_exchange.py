@@ -269,7 +269,9 @@ def test_src_blocked_reduction(monkeypatch, n_blocks, dtype, F):
     for b in range(n_blocks):
         s_b, d_b = bl.src_index[bl.bounds[b]:bl.bounds[b + 1]].cpu(), bl.dst_index[bl.bounds[b]:bl.bounds[b + 1]].cpu()
         assert bool(((s_b >= b * per) & (s_b < (b + 1) * per)).all()) and bool((d_b[1:] >= d_b[:-1]).all())
-    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    # a 16-bit output is rounded once per pass (the passes accumulate INTO it): 2^-8 per pass at most; the automatic
+    # rule therefore blocks 4- and 8-byte element types only, and a forced count on bf16 is held to that bound
+    tol = 2.0 ** -8 * n_blocks if dtype == torch.bfloat16 else 1e-5
     plan = abi.DevicePlan(di, S)
     for reduce in ("sum", "mean"):
         for ww, wc in ((None, None), (w, w_c)):

@@ -36,7 +36,7 @@ cudaError_t launch_pf(const Params &p, const Shape &sh, cudaStream_t stream) {
 // Ring variants built.  Production: the lean ring (kLeanFlag + depth; depths GEOT_LEAN_A / _B, clamped to what the
 // batch allows) for the sum kernels with fp32 accumulators and at most one weight per edge, and the first-generation
 // ring (GEOT_PF_A / _B = depths 2 and 3) for what the lean ring does not serve (fp64, per-head weights) and as the
-// A/B reference (GEOT_B200_RING=2).  Tuning builds override the lists; 16 + depth selects the TMA-filled ring.
+// A/B reference (GEOT_B200_RING=2).  Tuning builds override the lists.
 #ifndef GEOT_PF_A
 #define GEOT_PF_A 2
 #define GEOT_PF_B 3
@@ -61,19 +61,23 @@ cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
           constexpr int SB = ShapeOf<T, VECW, LPR, VPL, kLeanFlag | 1>::SB;
           constexpr int DA = lean_depth(GEOT_LEAN_A, SB), DB = lean_depth(GEOT_LEAN_B, SB);
           static_assert(DA >= 1 && DB >= 1, "a batch has at least two sub-batches");
-          const int want = pf & (kTmaFlag - 1);
+          const int want = pf & kDepthMask;
+          // the instantiation with the segment_reduce_ex options only when the call uses one of them
+          const bool ext = p.accumulate || p.zero_gaps || p.edge_perm != nullptr || p.mean_rowptr != nullptr;
           if (want > DA && DB != DA && ShapeOf<T, VECW, LPR, VPL, kLeanFlag | DB>::max_blocks >= 1)
-            return launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DB>(p, sh, stream);
+            return ext ? launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | kExtFlag | DB>(p, sh, stream)
+                       : launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DB>(p, sh, stream);
           if (ShapeOf<T, VECW, LPR, VPL, kLeanFlag | DA>::max_blocks >= 1)
-            return launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DA>(p, sh, stream);
+            return ext ? launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | kExtFlag | DA>(p, sh, stream)
+                       : launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DA>(p, sh, stream);
         }
       }
       pf = (VPL == 1) ? GEOT_PF_B : GEOT_PF_A;    // not served by the lean ring: first-generation ring (depth 3; 2 for rows >= 1 KB)
     }
     constexpr int U = ShapeOf<T, VECW, LPR, VPL, 1>::U;   // ring sub-batch
     constexpr int PFMAX = LPR / U;
-    // a list entry is depth (+ kTmaFlag for the TMA-filled ring); the depth is clamped to what the batch allows
-#define GEOT_CLAMP_PF(X) ((((X) & (kTmaFlag - 1)) < PFMAX ? ((X) & (kTmaFlag - 1)) : PFMAX) | ((X) & kTmaFlag))
+    // a list entry is a depth, clamped to what the batch allows
+#define GEOT_CLAMP_PF(X) (((X) & kDepthMask) < PFMAX ? ((X) & kDepthMask) : PFMAX)
     constexpr int PFA = GEOT_CLAMP_PF(GEOT_PF_A);
     if (pf == GEOT_PF_A && ShapeOf<T, VECW, LPR, VPL, PFA>::max_blocks >= 1)
       return launch_pf<T, VECW, LPR, VPL, RED, WM, PFA>(p, sh, stream);
@@ -137,10 +141,22 @@ cudaError_t GEOT_CAT(launch_, GEOT_TN, GEOT_RED)(const Params &p, const Shape &s
   else return cudaErrorInvalidValue;
   if (ev1) cudaEventRecord(ev1, stream);
   if (e != cudaSuccess) return e;
-  // second pass: segments cut by tile boundaries
+  // second pass: segments cut by tile boundaries.  Programmatic dependent launch: the fixup grid is set up while the
+  // main kernel is still running and its CTAs start at griddepcontrol.wait, which returns when the main grid has
+  // completed and its writes are visible -- the launch gap between the two kernels (a third of the step on the small
+  // BASELINE shapes) overlaps the main kernel's tail.
   const unsigned blocks = (unsigned)((p.n_tiles + (kThreads / 32) - 1) / (kThreads / 32));
-  segment_fixup_kernel<T, GEOT_RED><<<blocks, kThreads, 0, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, segment_fixup_kernel<T, GEOT_RED>, p);
 }
 
 }  // namespace geot

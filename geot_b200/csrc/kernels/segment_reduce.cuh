@@ -154,10 +154,11 @@ template <> __device__ __forceinline__ float ld_stream_t<float>(const float *p, 
 //            bypassed): PF sub-batches of U rows are in flight while one is consumed, so the bytes in flight
 //            are bounded by shared memory (up to ~128 KB per SM) instead of by registers.  Every lane reads
 //            back only the 16-byte pieces it copied itself: cp.async.wait_group is the only synchronisation.
-//   PF >= 16: the same ring filled by TMA bulk copies (cp.async.bulk.shared.global, UBLKCP) of depth PF - 16:
-//            lane k issues ONE copy for the whole row of edge k (no offset shuffles, no per-lane LDGSTS, the
-//            L1/LSU path is not involved); completion is an mbarrier transaction count per ring stage.
-constexpr int kTmaFlag = 16;
+//   (Two TMA-filled rings were built and measured, then removed: one 1-D bulk copy per row (cp.async.bulk, UBLKCP) was
+//   15-40 % slower than cp.async at 256 B - 1 KB rows (profiles/r01_ring_sweep_run3_tma.txt), and Blackwell's gather4
+//   (cp.async.bulk.tensor.2d...tile::gather4, UTMALDG.2D.GATHER4: 4 rows per instruction) 3x slower on Reddit gws
+//   (11.5 vs 3.9 ms, profiles/r02e_sass_gather4_ring.txt): the TMA unit serialises the row fetches of a gather.)
+constexpr int kDepthMask = 15;
 //   PF & 32 (kLeanFlag): the LEAN ring -- the same cp.async ring with the per-edge bookkeeping moved out of the
 //            instruction stream.  The batch's src row ids (32 bit: a ring row is >= 128 bytes, so any valid row id
 //            of a 180 GB device fits) and weights are parked in a small per-group shared-memory buffer and come
@@ -167,15 +168,19 @@ constexpr int kTmaFlag = 16;
 //            instructions per 512-byte row instead of 32 (profiles/r01c_*).  sum kernels with fp32 accumulators,
 //            no per-head weights, chunks that are whole batches.
 constexpr int kLeanFlag = 32;
+//   PF & 64 (kExtFlag, lean ring only): the instantiation that honours the options of geot_b200_segment_reduce_ex
+//            (accumulate, zero_gaps, edge_perm, mean_rowptr).  The plain instantiation has none of that code: measured
+//            5 % (Reddit gws) to 10 % (products gs64) faster than carrying the unused branches
+//            (profiles/r02e_tune_ext_ab_gather4_ab.txt), so the launcher picks per call.
+constexpr int kExtFlag = 64;
 //   (A "lean register path" -- the same bookkeeping with the rows loaded straight into double-buffered registers, so
 //   that a gathered byte crosses the L1TEX data pipe once -- was built and measured in round 2: 15-25 % SLOWER than the
 //   ring on every gather workload, profiles/r02a_ring96_ab.txt; too few bytes in flight per SM.  Removed.)
 template <typename T, int VECW, int LPR, int VPL, int PF_>
 struct ShapeOf {
   using A = typename AccOf<T>::type;
-  static constexpr bool TMA = (PF_ & kTmaFlag) != 0;
   static constexpr bool LEAN = (PF_ & kLeanFlag) != 0;   // the lean ring
-  static constexpr int PF = PF_ & (kTmaFlag - 1);       // ring depth
+  static constexpr int PF = PF_ & kDepthMask;           // ring depth
   static constexpr int NG = kThreads / LPR;      // chunks (groups) per tile
   static constexpr int CW = LPR * VPL * VECW;    // columns per CTA
   // ring: 4 rows per sub-batch (2 for the widest rows) measured best on B200 (profiles/r01_ring_sweep.md)
@@ -194,8 +199,7 @@ struct ShapeOf {
   static constexpr size_t ops_bytes = LEAN ? (size_t)NG * 4 * LPR * 4 : 0;
   static constexpr size_t ring_off = carry_bytes + ops_bytes;
   static constexpr size_t ring_bytes = PF > 0 ? (size_t)NG * NS * U * CW * sizeof(T) : 0;
-  static constexpr size_t bar_bytes = TMA ? (((size_t)NG * NS * 8 + 127) & ~(size_t)127) : 0;   // one mbarrier per (group, stage)
-  static constexpr size_t smem_bytes = ring_off + ring_bytes + bar_bytes;
+  static constexpr size_t smem_bytes = ring_off + ring_bytes;
   static constexpr int max_blocks = (int)((227 * 1024) / (smem_bytes + 1024));
   static constexpr int min_blocks_direct = (VPL == 1 ? GEOT_MINB : (VPL == 2 && VECW * sizeof(T) <= 16 ? 2 : 1));
   static constexpr int min_blocks = PF == 0 ? min_blocks_direct : (max_blocks >= 3 ? 3 : (max_blocks >= 2 ? 2 : 1));
@@ -213,30 +217,6 @@ __device__ __forceinline__ const char *row_addr(const char *base, uint32_t row, 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// mbarrier + TMA bulk copy (1-D): global -> this CTA's shared memory, completion counted in bytes on the barrier
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *gptr, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(gptr), "r"(bytes), "r"(bar)
-               : "memory");
-}
 
 // Rows [lo, hi) receive no edge: they read 0.  A cold path (the jump in dst_index is seen by one group), kept out of
 // line so that the close-a-row code of the main kernel stays small.
@@ -266,13 +246,10 @@ template <typename A> __device__ __forceinline__ A div_by_count(A v, A n, A n_in
 
 template <typename T, int VECW, int LPR, int VPL, int RED, int WM, int PF_>
 __global__ void __launch_bounds__(kThreads, (ShapeOf<T, VECW, LPR, VPL, PF_>::min_blocks))
-segment_reduce_kernel(const Params p) {
-  // the options of geot_b200_segment_reduce_ex (GEOT_NO_EXT: a tuning build without them, to measure what they cost)
-#ifdef GEOT_NO_EXT
-  constexpr bool kExt = false;
-#else
-  constexpr bool kExt = true;
-#endif
+segment_reduce_kernel(const __grid_constant__ Params p) {
+  // the options of geot_b200_segment_reduce_ex: always compiled in, except in the plain lean-ring instantiation
+  constexpr bool kExt = !ShapeOf<T, VECW, LPR, VPL, PF_>::LEAN || (PF_ & kExtFlag) != 0;
+  asm volatile("griddepcontrol.launch_dependents;");      // the fixup grid may be set up now; it waits for this grid to finish
   const bool o_accumulate = kExt && p.accumulate != 0;
   const bool o_zero_gaps = kExt && p.zero_gaps != 0;
   const int64_t *const o_mean_rowptr = kExt ? p.mean_rowptr : nullptr;
@@ -281,7 +258,6 @@ segment_reduce_kernel(const Params p) {
   using VecT = Vec<T, VECW>;
   using SH = ShapeOf<T, VECW, LPR, VPL, PF_>;
   constexpr int PF = SH::PF;
-  constexpr bool TMA = SH::TMA;
   constexpr bool LEAN = SH::LEAN;
   constexpr int NG = SH::NG;      // chunks per tile
   constexpr int CW = SH::CW;      // columns per CTA
@@ -348,22 +324,10 @@ segment_reduce_kernel(const Params p) {
   // this group's ring: NS stages of U rows; lane piece j of row r at r*CW + (j*LPR + gl)*VECW
   T *ring = nullptr;
   uint32_t ring_s = 0;
-  uint32_t bars_s = 0;          // TMA: this group's NS mbarriers
   if constexpr (PF > 0) {
     ring = reinterpret_cast<T *>(smem_raw + SH::ring_off) + (size_t)g * (NS * U * CW) + gl * VECW;
     ring_s = (uint32_t)__cvta_generic_to_shared(ring);
   }
-  if constexpr (TMA) {
-    bars_s = (uint32_t)__cvta_generic_to_shared(smem_raw + SH::ring_off + SH::ring_bytes) + (uint32_t)(g * NS * 8);
-    if (gl == 0) {
-#pragma unroll
-      for (int q = 0; q < NS; ++q) mbar_init(bars_s + q * 8, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp(gmask);
-  }
-
   A acc[VPL][VECW];    // the open run
 #pragma unroll
   for (int j = 0; j < VPL; ++j)
@@ -623,28 +587,13 @@ segment_reduce_kernel(const Params p) {
       if (e_begin + LPR < e_end) load_batch(e_begin + LPR, (int)min((int64_t)LPR, e_end - e_begin - LPR), n_dst, n_off, n_w);
 
       // ring: copies sub-batch [kk, kk+U) of a batch (row offsets in `offs`, one per lane) into `stage`
-      // bytes of one row inside this CTA's column slab (TMA copies exactly the slab)
-      const uint32_t slab_bytes = (uint32_t)(min((int64_t)CW, W - col0) * (int64_t)sizeof(T));
-      const char *slab_src = reinterpret_cast<const char *>(src + col0);
-      uint32_t n_consumed = 0;    // TMA: sub-batches consumed so far (stage = n % NS, parity = (n / NS) & 1)
       auto ring_issue = [&](int64_t offs, int kk, int stage) {
-        if constexpr (TMA) {
-          // lane kk+u copies the row of edge kk+u (its own offset register) into slot (stage, u)
-          const uint32_t bar = bars_s + stage * 8;
-          if (gl == 0) mbar_expect_tx(bar, U * slab_bytes);
-          __syncwarp(gmask);          // every lane is done reading the slot's previous occupant; expect precedes the copies
-          const int u = gl - kk;
-          if (u >= 0 && u < U)
-            tma_load_1d(ring_s - (uint32_t)(gl * VECW * sizeof(T)) + (uint32_t)((stage * U + u) * CW * sizeof(T)), slab_src + offs,
-                        slab_bytes, bar);
-        } else {
   #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int64_t off = __shfl_sync(gmask, offs, kk + u, LPR);
+        for (int u = 0; u < U; ++u) {
+          const int64_t off = __shfl_sync(gmask, offs, kk + u, LPR);
   #pragma unroll
-            for (int j = 0; j < VPL; ++j)
-              cp_async_16(ring_s + (uint32_t)(((stage * U + u) * CW + j * LPR * VECW) * sizeof(T)), lane_src[j] + off);
-          }
+          for (int j = 0; j < VPL; ++j)
+            cp_async_16(ring_s + (uint32_t)(((stage * U + u) * CW + j * LPR * VECW) * sizeof(T)), lane_src[j] + off);
         }
       };
       int stage = 0;              // ring stage of the sub-batch consumed next
@@ -654,7 +603,7 @@ segment_reduce_kernel(const Params p) {
   #pragma unroll
         for (int q = 0; q < PF; ++q) {
           if (full0) ring_issue(my_off, q * U, q);
-          if constexpr (!TMA) cp_async_commit();
+          cp_async_commit();
         }
       }
 
@@ -691,13 +640,8 @@ segment_reduce_kernel(const Params p) {
               if (st >= NS) st -= NS;
               if (kk < LPR) ring_issue(my_off, kk, st);
               else if (next_full) ring_issue(n_off, kk - LPR, st);
-              if constexpr (TMA) {
-                mbar_wait(bars_s + stage * 8, (n_consumed / NS) & 1u);
-                ++n_consumed;
-              } else {
-                cp_async_commit();
-                cp_async_wait<PF>();
-              }
+              cp_async_commit();
+              cp_async_wait<PF>();
   #pragma unroll
               for (int u = 0; u < U; ++u) {
                 const A we = (WM == WM_EDGE) ? __shfl_sync(gmask, my_w, k0 + u, LPR) : A(1);
@@ -854,8 +798,10 @@ segment_reduce_kernel(const Params p) {
 // summation order.
 template <typename T, int RED>
 __global__ void __launch_bounds__(kThreads)
-segment_fixup_kernel(const Params p) {
+segment_fixup_kernel(const __grid_constant__ Params p) {
   using A = typename AccOf<T>::type;
+  // launched as a programmatic dependent of the main kernel (inst.cu): nothing of its output may be read before this
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   constexpr int NW = kThreads / 32;
   constexpr int kLong = 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

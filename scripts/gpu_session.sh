@@ -5,7 +5,8 @@
 # legs: test (pytest -m gpu) | smoke | bench (default bench.py, own + reference arm) | benchN (torchrun bench at N = all
 #       visible GPUs, own + reference arm) | exch (N > 1: products / reddit with every exchange form) | model (configs[4]
 #       at N GPUs) | launches (ncu launch list of the default bench) | ncu:<workload> (one --set full capture) |
-#       tune:<workload>[:chunks] | env:<NAME=VALUE> (exported for the legs that follow)
+#       tune:<workload>[:chunks] | compare (the reference's own CUDA kernels beside ours, sorted and sorted=False) |
+#       env:<NAME=VALUE> (exported for the legs that follow)
 TAG=$1; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -46,6 +47,9 @@ PY
     ncu:*) wl=${leg#ncu:}
       GEOT_B200_BENCH_SECONDARY=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:segment_reduce_kernel -s 3 -c 1 -o $OUT/prof_$wl \
         python bench.py --workload $wl --steps 3 --warmup 3 > $OUT/prof_$wl.log 2>&1; ls -la $OUT/prof_$wl.ncu-rep;;
+    compare) timeout 900 python scripts/compare_reference_cuda.py > $OUT/compare_reference.jsonl 2> $OUT/compare_reference.err
+      timeout 300 python scripts/compare_reference_cuda.py unsorted > $OUT/compare_unsorted.jsonl 2>> $OUT/compare_reference.err
+      cut -c1-400 $OUT/compare_reference.jsonl $OUT/compare_unsorted.jsonl; tail -3 $OUT/compare_reference.err;;
     tune:*) IFS=: read -r _ wl chunks <<< "$leg"
       timeout 300 python scripts/tune.py $wl ${chunks:-0} 2>&1 | grep -E "lib=|rror" | tee -a $OUT/tune.txt;;
     *) echo "unknown leg $leg";;

@@ -72,6 +72,17 @@ cudaError_t launch_wm(const Params &p, const Shape &sh, cudaStream_t stream) {
                        : launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | DA>(p, sh, stream);
         }
       }
+      if constexpr (WM == WM_GENERIC && sizeof(typename AccOf<T>::type) == 4) {
+        // per-head weights (mh_spmm): the lean ring with the weights parked [head][edge]; up to kHeadMax heads
+        if (p.chunk_edges % LPR == 0 && p.weight != nullptr && p.W / p.F <= kHeadMax && p.W % p.F == 0 && p.edge_perm == nullptr) {
+          constexpr int SB = ShapeOf<T, VECW, LPR, VPL, kLeanFlag | kHeadFlag | 1>::SB;
+          constexpr int DA = lean_depth(GEOT_LEAN_A, SB);
+          const bool ext = p.accumulate || p.zero_gaps || p.mean_rowptr != nullptr;
+          if (ShapeOf<T, VECW, LPR, VPL, kLeanFlag | kHeadFlag | DA>::max_blocks >= 1)
+            return ext ? launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | kHeadFlag | kExtFlag | DA>(p, sh, stream)
+                       : launch_pf<T, VECW, LPR, VPL, RED, WM, kLeanFlag | kHeadFlag | DA>(p, sh, stream);
+        }
+      }
       pf = (VPL == 1) ? GEOT_PF_B : GEOT_PF_A;    // not served by the lean ring: first-generation ring (depth 3; 2 for rows >= 1 KB)
     }
     constexpr int U = ShapeOf<T, VECW, LPR, VPL, 1>::U;   // ring sub-batch

@@ -173,6 +173,12 @@ constexpr int kLeanFlag = 32;
 //            5 % (Reddit gws) to 10 % (products gs64) faster than carrying the unused branches
 //            (profiles/r02e_tune_ext_ab_gather4_ab.txt), so the launcher picks per call.
 constexpr int kExtFlag = 64;
+//   PF & 128 (kHeadFlag, lean ring only): per-head weights (mh_spmm: weight[e, h], H <= kHeadMax heads).  The batch's
+//            weights are parked TRANSPOSED in the operand buffer, [head][edge], so that a lane reads the U weights of its
+//            own head for a sub-batch with one LDS.128 -- instead of one __ldg per edge and lane on the first-generation
+//            ring (arxiv-shape mh_spmm was 4x slower per edge than Reddit gws at the same row size).
+constexpr int kHeadFlag = 128;
+constexpr int kHeadMax = 8;
 //   (A "lean register path" -- the same bookkeeping with the rows loaded straight into double-buffered registers, so
 //   that a gathered byte crosses the L1TEX data pipe once -- was built and measured in round 2: 15-25 % SLOWER than the
 //   ring on every gather workload, profiles/r02a_ring96_ab.txt; too few bytes in flight per SM.  Removed.)
@@ -180,6 +186,7 @@ template <typename T, int VECW, int LPR, int VPL, int PF_>
 struct ShapeOf {
   using A = typename AccOf<T>::type;
   static constexpr bool LEAN = (PF_ & kLeanFlag) != 0;   // the lean ring
+  static constexpr bool HEADW = LEAN && (PF_ & kHeadFlag) != 0;   // ... with per-head weights
   static constexpr int PF = PF_ & kDepthMask;           // ring depth
   static constexpr int NG = kThreads / LPR;      // chunks (groups) per tile
   static constexpr int CW = LPR * VPL * VECW;    // columns per CTA
@@ -196,7 +203,9 @@ struct ShapeOf {
   static constexpr size_t scalars_off = (LEAN ? 1 : 2) * (size_t)NG * CW * sizeof(A);
   static constexpr size_t carry_bytes = ((scalars_off + (size_t)NG * (4 * 8 + 4)) + 127) & ~(size_t)127;
   // lean: per group two operand buffers of LPR src row ids + LPR weights
-  static constexpr size_t ops_bytes = LEAN ? (size_t)NG * 4 * LPR * 4 : 0;
+  // (per-head weights: two batches of kHeadMax x LPR weights instead of LPR)
+  static constexpr int ops_words = HEADW ? (2 * LPR + 2 * kHeadMax * LPR) : 4 * LPR;   // per group
+  static constexpr size_t ops_bytes = LEAN ? (size_t)NG * ops_words * 4 : 0;
   static constexpr size_t ring_off = carry_bytes + ops_bytes;
   static constexpr size_t ring_bytes = PF > 0 ? (size_t)NG * NS * U * CW * sizeof(T) : 0;
   static constexpr size_t smem_bytes = ring_off + ring_bytes;
@@ -264,7 +273,7 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
   constexpr int U = SH::U;        // row loads in flight per group (PF == 0) / rows per ring sub-batch
   constexpr int NS = SH::NS;
   static_assert(PF == 0 || VECW * sizeof(T) == 16, "the ring moves 16-byte pieces");
-  static_assert(!LEAN || (RED == RED_SUM && WM != WM_GENERIC), "lean ring: sum, at most one weight per edge");
+  static_assert(!LEAN || (RED == RED_SUM && (WM == WM_GENERIC) == SH::HEADW), "lean ring: sum; per-head weights in their own instantiation");
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   A *s_head = reinterpret_cast<A *>(smem_raw);              // [NG][CW]
@@ -419,19 +428,56 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
       const int n_edges = (int)(e_end - e_begin);
       const int nfull = n_edges / LPR;             // whole batches; a remainder only in the edge list's last chunk
       const int n_ring = nfull * LPR;              // edges that go through the ring
-      uint32_t *ids = reinterpret_cast<uint32_t *>(smem_raw + SH::carry_bytes) + g * (2 * RING_WORDS);   // src row ids
+      constexpr bool HEADW = SH::HEADW;            // per-head weights, parked [batch][head][edge]
+      constexpr int NW = HEADW ? kHeadMax : 1;     // weights a lane loads per edge
+      uint32_t *ids = reinterpret_cast<uint32_t *>(smem_raw + SH::carry_bytes) + g * SH::ops_words;      // src row ids
       float *wts = reinterpret_cast<float *>(ids + RING_WORDS);                                          // weights
       const uint32_t row_bytes32 = (uint32_t)p.W * (uint32_t)sizeof(T);
       uint32_t ld32 = (uint32_t)last_dst;          // dst row of the edge left of the current batch
+      const int Hn = HEADW ? (int)(p.W / p.F) : 1; // heads (<= kHeadMax: the launcher checked)
+      int hj[VPL];                                 // head of this lane's vector j
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) hj[j] = HEADW ? (int)((col_ok[j] ? col[j] : col0) / p.F) : 0;
+      // all H weights of an edge as one 16-byte load when they are contiguous and fill it ([E, H] layout)
+      const bool w_vec16 = HEADW && p.ws_h == 1 && p.ws_e == Hn && Hn * (int)sizeof(T) == 16 &&
+                           (reinterpret_cast<uintptr_t>(weight) & 15) == 0;
 
-      // this lane's operands of batch bi: dst row, src row id, weight
-      auto ld_ops = [&](int bi, uint32_t &d, uint32_t &sid, float &wv) {
+      // this lane's operands of batch bi: dst row, src row id, weight(s)
+      auto ld_ops = [&](int bi, uint32_t &d, uint32_t &sid, float(&wv)[NW]) {
         const int64_t e = e_begin + (int64_t)bi * LPR + gl;
         d = (uint32_t)ld_stream(dst_index + e, pol);
         sid = src_index ? (uint32_t)ld_stream(src_index + e, pol) : (uint32_t)e;
-        wv = 1.f;
-        if (WM == WM_EDGE) wv = to_acc<T>(ld_stream_t<T>(weight + (o_edge_perm ? (int64_t)ld_stream32(o_edge_perm + e, pol) : e), pol));
+#pragma unroll
+        for (int h = 0; h < NW; ++h) wv[h] = 1.f;
+        if constexpr (HEADW) {
+          if (w_vec16) {
+            constexpr int PER = 16 / (int)sizeof(T);
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(weight + e * PER));
+            const Vec<T, PER> t = *reinterpret_cast<const Vec<T, PER> *>(&raw);
+#pragma unroll
+            for (int h = 0; h < PER && h < NW; ++h) wv[h] = to_acc<T>(t.v[h]);
+          } else {
+#pragma unroll
+            for (int h = 0; h < NW; ++h)
+              if (h < Hn) wv[h] = to_acc<T>(ld_stream_t<T>(weight + e * p.ws_e + h * p.ws_h, pol));
+          }
+        } else if (WM == WM_EDGE) {
+          wv[0] = to_acc<T>(ld_stream_t<T>(weight + (o_edge_perm ? (int64_t)ld_stream32(o_edge_perm + e, pol) : e), pol));
+        }
       };
+      // parks this lane's operands of a batch in operand buffer half b (0 / 1)
+      auto park_ops = [&](int b, uint32_t sid, const float(&wv)[NW]) {
+        ids[b * LPR + gl] = sid;
+        if constexpr (HEADW) {
+#pragma unroll
+          for (int h = 0; h < NW; ++h)
+            if (h < Hn) wts[(b * kHeadMax + h) * LPR + gl] = wv[h];
+        } else {
+          wts[b * LPR + gl] = wv[0];
+        }
+      };
+      // word offset in `wts` of the weights of (buffer half b, position k in the batch) for this lane's vector j
+      auto w_at = [&](int b, int k, int j) -> int { return HEADW ? (b * kHeadMax + hj[j]) * LPR + k : b * LPR + k; };
       // copies the U rows whose ids are at o[0..U) into ring stage st (compile-time)
       auto issue = [&](const uint32_t *o, int st) {
         const Vec<uint32_t, U> r = *reinterpret_cast<const Vec<uint32_t, U> *>(o);
@@ -443,28 +489,26 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
                         row_addr(lane_src[j], r.v[u], row_bytes32));
         }
       };
-      auto add_edge = [&](const VecT(&v)[VPL], float we) {
+      auto add_edge = [&](const VecT(&v)[VPL], const float(&we)[VPL]) {
 #pragma unroll
         for (int j = 0; j < VPL; ++j)
 #pragma unroll
           for (int i = 0; i < VECW; ++i) {
             float x = to_acc<T>(v[j].v[i]);
-            if (WM != WM_NONE) x = x * we;
+            if (WM != WM_NONE) x = x * we[j];
             acc[j][i] = acc[j][i] + x;
           }
       };
 
       uint32_t d_cur = 0, d_nxt = 0, l_d = 0, l_s = 0;
-      float l_w = 1.f;
+      float l_w[NW];
       if (nfull > 0) {
         ld_ops(0, d_cur, l_s, l_w);
-        ids[gl] = l_s;
-        wts[gl] = l_w;
+        park_ops(0, l_s, l_w);
       }
       if (nfull > 1) {
         ld_ops(1, d_nxt, l_s, l_w);
-        ids[LPR + gl] = l_s;
-        wts[LPR + gl] = l_w;
+        park_ops(1, l_s, l_w);
       }
       __syncwarp(gmask);
       if (nfull > 0) {
@@ -499,10 +543,17 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
             if (pos + c < n_ring) issue(c < NS * U ? ids + blk + c : ids + blk_next + (c - NS * U), (t + PF) % NS);
             cp_async_commit();
             cp_async_wait<PF>();
-            Vec<float, U> wv;
+            // the U weights of this sub-batch (per vector of the lane when the weights are per head)
+            Vec<float, U> wv[VPL];
 #pragma unroll
-            for (int u = 0; u < U; ++u) wv.v[u] = 1.f;
-            if (WM == WM_EDGE) wv = *reinterpret_cast<const Vec<float, U> *>(wts + blk + t * U);
+            for (int j = 0; j < VPL; ++j) {
+#pragma unroll
+              for (int u = 0; u < U; ++u) wv[j].v[u] = 1.f;
+              if (WM != WM_NONE && (HEADW || j == 0))
+                wv[j] = *reinterpret_cast<const Vec<float, U> *>(wts + w_at(slot / LPR, (s0 + t) * U, j));
+              else if (WM != WM_NONE)
+                wv[j] = wv[0];
+            }
             VecT v[U][VPL];
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -513,7 +564,12 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
             bmask >>= U;
             if (sub == 0) {
 #pragma unroll
-              for (int u = 0; u < U; ++u) add_edge(v[u], wv.v[u]);
+              for (int u = 0; u < U; ++u) {
+                float we[VPL];
+#pragma unroll
+                for (int j = 0; j < VPL; ++j) we[j] = wv[j].v[u];
+                add_edge(v[u], we);
+              }
             } else {
               // a dst row starts inside these U edges: one edge at a time, operands re-read from shared memory
 #pragma unroll 1
@@ -532,7 +588,10 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
 #pragma unroll
                 for (int j = 0; j < VPL; ++j)
                   vv[j] = *reinterpret_cast<const VecT *>(ring + ((t * U + u) * CW + j * LPR * VECW));
-                add_edge(vv, WM == WM_EDGE ? wts[blk + t * U + u] : 1.f);
+                float we[VPL];
+#pragma unroll
+                for (int j = 0; j < VPL; ++j) we[j] = (WM != WM_NONE) ? wts[w_at(slot / LPR, (s0 + t) * U + u, j)] : 1.f;
+                add_edge(vv, we);
               }
             }
           }
@@ -540,10 +599,7 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
         }
         // this batch's operand buffer is free: park batch bi+2 there
         __syncwarp(gmask);
-        if (has_nn) {
-          ids[slot + gl] = l_s;
-          wts[slot + gl] = l_w;
-        }
+        if (has_nn) park_ops(slot / LPR, l_s, l_w);
         __syncwarp(gmask);
         slot ^= LPR;
         d_cur = d_nxt;
@@ -556,8 +612,13 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
         const int64_t e = e_begin + k;
         const uint32_t d = (uint32_t)dst_index[e];
         const int64_t sid = src_index ? src_index[e] : e;
-        float we = 1.f;
-        if (WM == WM_EDGE) we = to_acc<T>(weight[o_edge_perm ? (int64_t)o_edge_perm[e] : e]);
+        float we[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          we[j] = 1.f;
+          if (HEADW) we[j] = to_acc<T>(weight[e * p.ws_e + hj[j] * p.ws_h]);
+          else if (WM == WM_EDGE) we[j] = to_acc<T>(weight[o_edge_perm ? (int64_t)o_edge_perm[e] : e]);
+        }
         VecT v[VPL];
 #pragma unroll
         for (int j = 0; j < VPL; ++j) v[j] = *reinterpret_cast<const VecT *>(lane_src[j] + sid * row_bytes);

@@ -12,7 +12,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 N=$(nvidia-smi -L | wc -l)
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.max.mem --format=csv > $OUT/gpu.txt 2>&1
-trun() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 "$@"; }
+TRUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 for leg in "$@"; do
   echo "== leg $leg ($(date +%T))"
   case $leg in
@@ -24,12 +24,12 @@ for leg in "$@"; do
       timeout 900 python bench.py 2>$OUT/bench.err | tail -1 > $OUT/bench.json
       tail -3 $OUT/bench.err; cut -c1-600 $OUT/bench.json;;
     benchN)
-      timeout 600 trun bench.py --gpus $N --impl reference 2>$OUT/bench_n${N}_reference.err | tail -1 > $OUT/bench_n${N}_reference.json
-      timeout 900 trun bench.py --gpus $N 2>$OUT/bench_n$N.err | tail -1 > $OUT/bench_n$N.json
+      timeout 600 $TRUN bench.py --gpus $N --impl reference 2>$OUT/bench_n${N}_reference.err | tail -1 > $OUT/bench_n${N}_reference.json
+      timeout 900 $TRUN bench.py --gpus $N 2>$OUT/bench_n$N.err | tail -1 > $OUT/bench_n$N.json
       tail -3 $OUT/bench_n$N.err; cut -c1-600 $OUT/bench_n$N.json;;
     exch)
       for wl in reddit_gws products_gs64; do for ex in bucket push allgather replicated; do
-        GEOT_B200_BENCH_SECONDARY=0 GEOT_B200_EXCHANGE=$ex timeout 300 trun bench.py --gpus $N --workload $wl --steps 10 --warmup 3 \
+        GEOT_B200_BENCH_SECONDARY=0 GEOT_B200_EXCHANGE=$ex timeout 300 $TRUN bench.py --gpus $N --workload $wl --steps 10 --warmup 3 \
           2>$OUT/exch_${wl}_$ex.err | tail -1 > $OUT/exch_${wl}_$ex.json
         python - <<PY
 import json
@@ -40,7 +40,7 @@ except Exception as e:
     print("$wl $ex N=$N: FAILED", e)
 PY
       done; done 2>&1 | tee $OUT/exch.txt;;
-    model) timeout 600 trun scripts/bench_model_multi.py > $OUT/model_n$N.jsonl 2> $OUT/model_n$N.err; cut -c1-900 $OUT/model_n$N.jsonl; tail -3 $OUT/model_n$N.err;;
+    model) timeout 600 $TRUN scripts/bench_model_multi.py > $OUT/model_n$N.jsonl 2> $OUT/model_n$N.err; cut -c1-900 $OUT/model_n$N.jsonl; tail -3 $OUT/model_n$N.err;;
     launches)
       GEOT_B200_BENCH_SECONDARY=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
         python bench.py --steps 3 --warmup 3 > $OUT/bench_under_ncu.log 2>&1; grep -c geot $OUT/launches.csv;;

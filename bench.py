@@ -30,9 +30,10 @@ for index_scatter only -- numerically wrong, SURVEY 8a A5 -- and none for gather
 arm is the oracle port / torch restatement; where oracle/_ref was built its csrc/cpu kernel is timed too
 and labelled).  N > 1: one process per GPU under torchrun; the dst rows are sharded with balanced edge
 counts, each rank reduces its own slice, the src rows travel each step inside the timed region
-(GEOT_B200_EXCHANGE = bucket [default: all-gather on a side stream overlapped with the src-local edge
-bucket, src-remote bucket accumulated afterwards] | push [needed rows stored into the peers' symmetric
-memory by one kernel] | allgather [one all-gather, then one reduction] | replicated; strong scaling).
+(GEOT_B200_EXCHANGE = push [default: the rows the peers' edges reference are stored into their symmetric
+memory by one kernel, overlapped with the src-local edge bucket; src-remote bucket accumulated afterwards]
+| bucket [the same two buckets around one NCCL all-gather] | allgather [one all-gather, then one
+reduction] | replicated; strong scaling).
 """
 import argparse
 import json
@@ -304,7 +305,9 @@ class Runner:
             if self.exchange == "replicated":
                 gdist.all_gather_rows(self.x_local, rb, out=self.x_full)
             if self.exchange in ("bucket", "push"):
-                self.bg = gdist.BucketedGather(sh, transport="push" if self.exchange == "push" else "allgather")
+                # passes: 0 = the library's choice (two overlapped passes when the local bucket's rows are long, else one)
+                self.bg = gdist.BucketedGather(sh, transport="push" if self.exchange == "push" else "allgather",
+                                               passes=int(os.environ.get("GEOT_B200_EXCHANGE_PASSES", "0")))
                 self.exchanged = self.bg.exchanged_rows()
         else:
             self.di, self.si, self.w, self.S, self.row0 = wk["di"], wk["si"], w, wk["S"], 0
@@ -324,7 +327,8 @@ class Runner:
                     self.blocks = abi.SrcBlocks(self.si, self.di, wk["N"], nb)
             self.ws = abi.Workspace(self.E, self.W, wk["dtype"], dev, src_blocks=self.blocks)
         self.n_blocks = self.blocks.n_blocks if self.blocks is not None else 1
-        self.calls_per_step = 2 if self.bg is not None else self.n_blocks
+        self.passes = self.bg.passes if self.bg is not None else 1
+        self.calls_per_step = self.passes if self.bg is not None else self.n_blocks
         per_head_perm = 1 if (self.bg is not None and w is not None and w.dim() == 2) else 0
         # this library's kernels per step: main + fixup per reduction (+ the push kernel, + the per-head weight permutation)
         self.launches_per_step = 2 * self.calls_per_step + (1 if self.exchange == "push" else 0) + per_head_perm
@@ -488,7 +492,7 @@ def summarize(wk, r, ms, kmean, peak, parity, world):
          "edges_per_s": wk["E"] / (ms * 1e-3), "kernel_ms": round(kmean, 4), "kernel_achieved_gbs": round(achieved, 1),
          "frac_of_measured_hbm": round(wk["bytes_logical"] / (ms * 1e-3) / 1e9 / peak, 4),
          "bytes_logical_per_step": wk["bytes_logical"], "bytes_compulsory_per_step": wk["bytes_compulsory"],
-         "traffic": traffic, "exchange": r.exchange, "src_blocks": r.n_blocks, "parity": parity}
+         "traffic": traffic, "exchange": r.exchange, "exchange_passes": r.passes, "src_blocks": r.n_blocks, "parity": parity}
     d.update(f)
     return d
 
@@ -637,7 +641,7 @@ def run_own(args):
     import geot_b200  # noqa: F401
 
     peak, peak_src = measured_peak_gbs()
-    exchange = os.environ.get("GEOT_B200_EXCHANGE", "bucket")
+    exchange = os.environ.get("GEOT_B200_EXCHANGE", "push")
     if exchange not in ("bucket", "push", "allgather", "replicated"):
         raise SystemExit("GEOT_B200_EXCHANGE must be bucket, push, allgather or replicated")
     wk = build_workload(args.workload, dev)
@@ -663,6 +667,9 @@ def run_own(args):
     cfg = config_of(wk, world, r.exchange)
     cfg["src_blocks"] = ("%d (the edge list regrouped once per graph by src-row block for the L2; one pass per block, later passes "
                          "accumulate)" % r.n_blocks) if r.n_blocks > 1 else "1 (one pass)"
+    if r.bg is not None:
+        cfg["exchange_passes"] = ("%d (%s)" % (r.passes, "src-local bucket overlapped with the exchange, src-remote bucket accumulated"
+                                                 if r.passes == 2 else "exchange, then one reduction over own + received rows"))
     meta = dict(metric=metric_name(wk), dtype=DTYPE_NAME[wk["dtype"]], config=cfg, E=wk["E"],
                 launches=r.launches_per_step, exchange=r.exchange, imbalance=r.imbalance, exchanged=r.exchanged)
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
     "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_permute_edges",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
-    "geot_b200_l2_persist", "geot_b200_l2_persist_reset", "geot_b200_push_rows",
+    "geot_b200_push_rows",
     "geot_b200_host_last_transfer", "geot_b200_host_row_pointers", "geot_b200_segment_reduce_ex",
     "geot_b200_host_graph_create", "geot_b200_host_graph_reduce", "geot_b200_host_graph_last_transfer",
     "geot_b200_host_graph_destroy", "geot_b200_src_blocks_suggest", "geot_b200_src_blocks_bytes",
@@ -102,8 +102,6 @@ def lib() -> ctypes.CDLL:
         L.geot_b200_csr_to_coo.argtypes = [vp, ci, i64, i64, vp, vp]
         L.geot_b200_permute_edges.argtypes = [vp, vp, vp, i64, i64, vp]
         L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
-        L.geot_b200_l2_persist.argtypes = [vp, sz, vp, ctypes.POINTER(sz), ctypes.POINTER(sz)]
-        L.geot_b200_l2_persist_reset.argtypes = [vp]
         L.geot_b200_push_rows.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, vp]
         L.geot_b200_host_last_transfer.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
         L.geot_b200_host_row_pointers.argtypes = [vp, i64, i64, i64, vp, ci]
@@ -121,19 +119,6 @@ def profile_read(capacity: int = 4096):
     cnt = ctypes.c_int(0)
     check(lib().geot_b200_profile_read(buf, capacity, ctypes.byref(cnt)), "profile_read")
     return [buf[i] for i in range(cnt.value)]
-
-
-def l2_persist(t: torch.Tensor):
-    """Pins tensor ``t`` (the src feature matrix of a gather op) in the persisting L2 set-aside for kernels launched on
-    the current stream (geot_b200_l2_persist).  Returns (window_bytes, carveout_bytes)."""
-    win, carve = ctypes.c_size_t(0), ctypes.c_size_t(0)
-    check(lib().geot_b200_l2_persist(_ptr(t), t.numel() * t.element_size(), _stream(), ctypes.byref(win),
-                                     ctypes.byref(carve)), "l2_persist")
-    return win.value, carve.value
-
-
-def l2_persist_reset() -> None:
-    check(lib().geot_b200_l2_persist_reset(_stream()), "l2_persist_reset")
 
 
 class AbiError(RuntimeError):

@@ -58,10 +58,6 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok,
   if (nvec <= 32) {
     lpr = pow2ceil(nvec);
     vpl = 1;
-    // experiment knob: narrower groups sweep the row in column slabs (the slab is the slow grid index), which
-    // shrinks the gathered working set per sweep at the price of re-reading the index streams
-    const int cap = env_int("GEOT_B200_LPR", 0);
-    if (cap >= 1 && cap < lpr) lpr = pow2ceil(cap);
   } else {
     // wider rows: several vectors per lane, capped so that the accumulators stay within 16 registers
     // (fp32: 4 vectors, fp64: 4, bf16/fp16 with 8-element vectors: 2); beyond that, column tiles
@@ -639,41 +635,6 @@ int geot_b200_profile_read(float *ms, int capacity, int *count) {
     CUDA_TRY(cudaEventElapsedTime(&ms[i], g_prof.start[slot], g_prof.stop[slot]));
   }
   *count = k;
-  return GEOT_OK;
-}
-
-// ---- L2 residency hint --------------------------------------------------------------------------------
-int geot_b200_l2_persist(const void *ptr, size_t bytes, cudaStream_t stream, size_t *window_bytes, size_t *carveout_bytes) {
-  if (!ptr || bytes == 0) return GEOT_ERR_INVALID_ARG;
-  int dev = 0, max_persist = 0, max_window = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
-  CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-  if (max_persist <= 0 || max_window <= 0) return GEOT_ERR_UNSUPPORTED;
-  CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
-  const size_t win = std::min(bytes, (size_t)max_window);
-  cudaStreamAttrValue v;
-  memset(&v, 0, sizeof(v));
-  v.accessPolicyWindow.base_ptr = const_cast<void *>(ptr);
-  v.accessPolicyWindow.num_bytes = win;
-  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
-  if (window_bytes) *window_bytes = win;
-  if (carveout_bytes) *carveout_bytes = (size_t)max_persist;
-  return GEOT_OK;
-}
-
-int geot_b200_l2_persist_reset(cudaStream_t stream) {
-  cudaStreamAttrValue v;
-  memset(&v, 0, sizeof(v));
-  v.accessPolicyWindow.num_bytes = 0;   // a window of 0 bytes disables the policy
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-  CUDA_TRY(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
-  CUDA_TRY(cudaCtxResetPersistingL2Cache());
-  CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));   // give the set-aside back to normal caching
   return GEOT_OK;
 }
 

@@ -16,7 +16,9 @@ Forms of the exchange:
   local bucket (writing every row of the output, rows without local edges as zeros); when the rows have landed the
   remote bucket is reduced with ``accumulate`` (``dst += partial``, ``geot_b200_segment_reduce_ex``).  The host cost
   is the same whatever the GPU count: 1 exchange + 2 reductions, no combine pass, no per-call weight permutation
-  (the kernel reads ``weight[edge_perm[e]]``).  Two transports:
+  (the kernel reads ``weight[edge_perm[e]]``).  When the rows of the local bucket would be short (products-shape
+  shards) the two passes cost more than the overlap buys and the op runs as ONE pass after the exchange over a buffer
+  that holds the own and the received rows (``passes``; chosen from the local bucket's degree).  Two transports:
 
   - ``"allgather"``: one ragged NCCL all-gather into the ``[N, ...]`` replica buffer;
   - ``"push"``: only the rows a peer's edges actually reference, stored by ONE kernel straight into the requesters'
@@ -192,9 +194,10 @@ def split_local_remote(shard: GraphShard):
     return perm, n_local
 
 
-def build_needed_rows(shard: GraphShard, remote_src: torch.Tensor, group=None):
+def build_needed_rows(shard: GraphShard, remote_src: torch.Tensor, group=None, own_rows_first: bool = False):
     """One-time request exchange of the push transport.  ``remote_src``: the global src ids of the rank's remote-src
-    edges.  Returns (NeededRows, compact ids of those edges into the receive buffer).
+    edges.  Returns (NeededRows, compact ids of those edges into the receive buffer).  ``own_rows_first``: every
+    rank's buffer starts with its own rows (single-pass form), the received rows follow.
 
     Collectives: one all-gather of the [world] request counts and offsets, then ``world-1`` staggered send/recv steps
     of the request lists (works on NCCL and gloo alike)."""
@@ -236,14 +239,19 @@ def build_needed_rows(shard: GraphShard, remote_src: torch.Tensor, group=None):
         lists.append(lst)
         # my rows for `to` land at the offset of ITS step k (owner = me) in its receive buffer
         n = send_counts[to]
+        base = (rb[to + 1] - rb[to]) if own_rows_first else 0
         peers.append(torch.full((n,), to, dtype=torch.int32))
-        slots.append(int(table[to][world + k - 1]) + torch.arange(n, dtype=torch.int64))
+        slots.append(base + int(table[to][world + k - 1]) + torch.arange(n, dtype=torch.int64))
     send_rows = torch.cat(lists) if lists else torch.empty(0, dtype=idt, device=dev)
     n_local = rb[rank + 1] - rb[rank]
     assert send_rows.numel() == 0 or (int(send_rows.min()) >= 0 and int(send_rows.max()) < n_local)
     dest_peer = (torch.cat(peers) if peers else torch.empty(0, dtype=torch.int32)).to(dev)
     dest_row = (torch.cat(slots) if slots else torch.empty(0, dtype=torch.int64)).to(dev)
-    buffer_rows = max(int(table[:, 2 * world].max()), 1)
+    if own_rows_first:
+        compact += n_local
+        buffer_rows = max(max(int(table[g][2 * world]) + rb[g + 1] - rb[g] for g in range(world)), 1)
+    else:
+        buffer_rows = max(int(table[:, 2 * world].max()), 1)
     nd = NeededRows(recv_counts, recv_offsets, send_counts, send_rows.contiguous(), dest_peer, dest_row, buffer_rows)
     return nd, compact
 
@@ -267,9 +275,14 @@ class BucketedGather:
       ``allocator(shape, dtype, device) -> (buffer, handle)``; ``pusher(x_local, nd, buffer, handle)``;
       ``barrier(handle, channel)``."""
 
+    # two passes pay when the rows of the local bucket are long enough that closing every dst row twice (and adding
+    # into it) costs less than the overlap buys: Reddit-shape shards (61 local edges per row at 8 GPUs) yes,
+    # products-shape ones (3) no -- measured at N = 2, profiles/r02g_n2_exch.txt
+    MIN_LOCAL_DEGREE = 16
+
     def __init__(self, shard: GraphShard, group=None, transport: str = "allgather", reducer=None, allocator=None,
-                 pusher=None, barrier=None):
-        assert transport in ("allgather", "push")
+                 pusher=None, barrier=None, passes: int = 0):
+        assert transport in ("allgather", "push") and passes in (0, 1, 2)
         assert shard.src_index is not None
         self.shard, self.group, self.transport = shard, group, transport
         self.world, self.rank = shard.world_size, shard.rank
@@ -279,14 +292,32 @@ class BucketedGather:
         E = shard.dst_index.numel()
         assert E < 2 ** 31, "edge_perm is int32"
         perm, n_local = split_local_remote(shard)
-        src = shard.src_index[perm]
-        src[:n_local] -= rb[rank]                          # bucket 0 reads the rank's own rows
+        if passes == 0:
+            # the same choice on every rank (the transports are collective): decided on the total local-src edge count
+            t = torch.tensor([float(n_local), float(max(shard.num_local_rows, 1))], dtype=torch.float64, device=shard.dst_index.device)
+            if self.world > 1:
+                dist.all_reduce(t, group=group)
+            passes = 2 if t[0].item() / t[1].item() >= self.MIN_LOCAL_DEGREE else 1
+        self.passes = passes
         self.needed = None
-        if transport == "push":
-            self.needed, compact = build_needed_rows(shard, src[n_local:].clone(), group)
-            src[n_local:] = compact
-        self.buckets = SrcBuckets(perm.to(torch.int32).contiguous(), [0, n_local, E], src.contiguous(),
-                                  shard.dst_index[perm].contiguous())
+        if passes == 1:
+            # single pass: the shard's edge list as it is (no permutation), src ids into ONE buffer that holds the own
+            # rows and the received ones -- the [N, ...] replica (all-gather) or [own rows | needed rows] (push)
+            src = shard.src_index.clone()
+            if transport == "push":
+                remote = (src < rb[rank]) | (src >= rb[rank + 1])
+                self.needed, compact = build_needed_rows(shard, src[remote], group, own_rows_first=True)
+                src[~remote] -= rb[rank]
+                src[remote] = compact
+            self.buckets = SrcBuckets(None, [0, E, E], src.contiguous(), shard.dst_index)
+        else:
+            src = shard.src_index[perm]
+            src[:n_local] -= rb[rank]                      # bucket 0 reads the rank's own rows
+            if transport == "push":
+                self.needed, compact = build_needed_rows(shard, src[n_local:].clone(), group)
+                src[n_local:] = compact
+            self.buckets = SrcBuckets(perm.to(torch.int32).contiguous(), [0, n_local, E], src.contiguous(),
+                                      shard.dst_index[perm].contiguous())
         self._plans, self._ws, self._bufs, self._mean_rowptr, self._wperm = {}, {}, {}, None, None
         self._replica = None
         self.comm_stream = torch.cuda.Stream() if self.cuda else None
@@ -314,7 +345,7 @@ class BucketedGather:
             if not accumulate:
                 out.zero_()
             return
-        si, di, perm = b.src_index[e0:e1], b.dst_index[e0:e1], b.perm[e0:e1]
+        si, di, perm = b.src_index[e0:e1], b.dst_index[e0:e1], (b.perm[e0:e1] if b.perm is not None else None)
         mean_rowptr = None
         if reduce == "mean":
             if self._mean_rowptr is None:
@@ -342,8 +373,9 @@ class BucketedGather:
                 nb = abi.src_blocks_suggest(e1 - e0, S, x.shape[0], W * x.element_size())
             if nb > 1:
                 blocks = abi.SrcBlocks(si, di, x.shape[0], nb)
-                blocks.composed_perm = perm[blocks.edge_perm.long()].contiguous()
-                blocks.c.edge_perm = blocks.composed_perm.data_ptr()
+                if perm is not None:
+                    blocks.composed_perm = perm[blocks.edge_perm.long()].contiguous()
+                    blocks.c.edge_perm = blocks.composed_perm.data_ptr()
             self._ws[key] = (abi.Workspace(e1 - e0, W, x.dtype, x.device, src_blocks=blocks), blocks)
         ws, blocks = self._ws[key]
         if blocks is not None:
@@ -351,11 +383,14 @@ class BucketedGather:
                                accumulate=accumulate, mean_rowptr=mean_rowptr, src_blocks=blocks)
             return
         abi.segment_reduce(x, si, di, weight, reduce, S=S, H=H, plan=self._plans[k], out=out, workspace=ws,
-                           accumulate=accumulate, edge_perm=perm if weight is not None else None, mean_rowptr=mean_rowptr)
+                           accumulate=accumulate, edge_perm=perm if weight is not None else None,
+                           mean_rowptr=mean_rowptr if self.passes == 2 else None)
 
     def _bucket_order(self, weight):
         """Per-head weights [E, H] in bucket order (one permutation pass per call: the kernel's edge_perm serves one
         weight per edge only)."""
+        if self.buckets.perm is None:
+            return weight
         from . import abi
         if self._wperm is None or self._wperm.shape != weight.shape or self._wperm.dtype != weight.dtype:
             self._wperm = torch.empty_like(weight)
@@ -394,6 +429,8 @@ class BucketedGather:
             all_gather_rows(x_local, self.shard.row_bounds, self.group, out=buf)
             return
         nd = self.needed
+        if self.passes == 1 and x_local.shape[0]:
+            buf[: x_local.shape[0]].copy_(x_local)          # the buffer starts with the rank's own rows
         self._barrier(hdl, 0)              # every peer is done reading its receive buffer (its previous call)
         if self._pusher is not None:       # (a stand-in also plays the receiving side: runs even with nothing to send)
             self._pusher(x_local, nd, buf, hdl)
@@ -419,6 +456,10 @@ class BucketedGather:
         if out is None:
             out = x_local.new_empty([S] + tail)
         buf, hdl = self._buffer(tail, x_local.dtype, x_local.device)
+        if self.passes == 1:               # nothing to overlap with: exchange, then ONE reduction over the buffer
+            self._exchange(x_local, buf, hdl)
+            self._reduce_bucket(0, buf, weight, out, reduce, accumulate=False)
+            return out
         if self.cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())   # x_local is final; buf's old rows were consumed
             with torch.cuda.stream(self.comm_stream):

@@ -244,22 +244,6 @@ GEOT_API int geot_b200_push_rows(const void *x, const int64_t *rows, const int32
                         void *const *peer_bases, int64_t n, int64_t row_bytes, int peers_aligned16,
                         cudaStream_t stream);
 
-/* ---- L2 residency hint (optional) --------------------------------------------------------------------------- */
-
-/* Marks [ptr, ptr + bytes) -- the src feature matrix of a gather op -- as the persisting L2 access-policy window of
- * `stream`: kernels launched on it afterwards keep those lines in the L2 set-aside while the read-once index /
- * weight streams pass through.  Sets the device's persisting-L2 carve-out to its maximum; the window is clipped to
- * the device's maximum window and the hit ratio scaled to carve-out / window when the matrix is larger.
- * *window_bytes / *carveout_bytes (optional) receive what was applied.  GEOT_ERR_UNSUPPORTED when the device has no
- * persisting L2.  Results never depend on it.  geot_b200_l2_persist_reset removes the window, resets the persisting
- * lines and returns the carve-out to normal caching.  Off unless the caller asks (bench.py: GEOT_B200_L2_PERSIST=1).
- * Measured on B200 (profiles/r01e_l2_persist_ab.txt): Reddit-shape gather_weight_scatter is SLOWER with the hint
- * (3.52 -> 4.08 ms: the 79 MB carve-out holds 70 % of the 119 MB matrix and the rest competes for what is left),
- * so no caller in this repo enables it by default. */
-GEOT_API int geot_b200_l2_persist(const void *ptr, size_t bytes, cudaStream_t stream, size_t *window_bytes,
-                         size_t *carveout_bytes);
-GEOT_API int geot_b200_l2_persist_reset(cudaStream_t stream);
-
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------------- */
 
 /* Same operation with every operand in HOST memory (pinned memory makes the copies asynchronous).

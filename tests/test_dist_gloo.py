@@ -75,7 +75,7 @@ def _worker(rank, world, port, q, hub=False):
     def reducer(xf, si, di, w, perm, S, out, accumulate, mean_rowptr, reduce):
         ww = None
         if w is not None:
-            ww = w[perm.long()] if w.dim() == 1 else w[perm.long()]
+            ww = w[perm.long()] if perm is not None else w        # (single pass: the shard's own edge order)
         part = oracle.segment_reduce(xf, si, di, ww, "sum", S=S, H=(xf.shape[1] if xf.dim() == 3 else 1))
         if reduce == "mean":
             deg = (mean_rowptr[1:] - mean_rowptr[:-1]).clamp_min(1).to(part.dtype)
@@ -87,6 +87,10 @@ def _worker(rank, world, port, q, hub=False):
 
     def check_buckets(bg):
         b = bg.buckets
+        if bg.passes == 1:
+            assert b.perm is None and b.bounds == [0, shard.num_local_edges, shard.num_local_edges]
+            assert torch.equal(b.dst_index, shard.dst_index)
+            return
         assert b.bounds[0] == 0 and b.bounds[2] == shard.num_local_edges and b.perm.dtype == torch.int32
         glob = shard.src_index[b.perm.long()]
         loc = (glob >= rb[rank]) & (glob < rb[rank + 1])
@@ -101,15 +105,19 @@ def _worker(rank, world, port, q, hub=False):
                 else oracle.gather_scatter(src_index, dst, x, reduce))
         return full[rb[rank]:rb[rank + 1]]
 
-    bg = gdist.BucketedGather(shard, transport="allgather", reducer=reducer)
-    check_buckets(bg)
-    assert torch.equal(bg.buckets.src_index[bg.buckets.bounds[1]:], shard.src_index[bg.buckets.perm.long()][bg.buckets.bounds[1]:])
-    for reduce in ["sum", "mean"]:
-        for weighted in (False, True):
-            got = bg(x_local.clone(), shard.weight if weighted else None, reduce)
-            assert torch.allclose(got, expect(reduce, weighted), rtol=1e-5, atol=1e-6), ("allgather", reduce, weighted)
-    buf, _ = bg._buffer([F], x.dtype, x.device)
-    assert torch.equal(buf, x)                                          # the exchange rebuilt the replica
+    auto = gdist.BucketedGather(shard, transport="allgather", reducer=reducer)
+    assert auto.passes in (1, 2)                                        # (chosen from the local bucket's degree, same on every rank)
+    for passes in (2, 1):
+        bg = gdist.BucketedGather(shard, transport="allgather", reducer=reducer, passes=passes)
+        check_buckets(bg)
+        if passes == 2:
+            assert torch.equal(bg.buckets.src_index[bg.buckets.bounds[1]:], shard.src_index[bg.buckets.perm.long()][bg.buckets.bounds[1]:])
+        for reduce in ["sum", "mean"]:
+            for weighted in (False, True):
+                got = bg(x_local.clone(), shard.weight if weighted else None, reduce)
+                assert torch.allclose(got, expect(reduce, weighted), rtol=1e-5, atol=1e-6), ("allgather", passes, reduce, weighted)
+        buf, _ = bg._buffer([F], x.dtype, x.device)
+        assert torch.equal(buf, x)                                      # the exchange rebuilt the replica
 
     # push transport: ONE push of the requested rows into slots of the requesters' buffers.  The stand-in pusher ships
     # (slot, row) pairs over gloo and the RECEIVER stores each row where the SENDER's slot says, so the slot arithmetic
@@ -140,7 +148,7 @@ def _worker(rank, world, port, q, hub=False):
     kw_push = dict(transport="push", reducer=reducer, pusher=pusher,
                    allocator=lambda shape, dtype, device: (torch.full(shape, float("nan"), dtype=dtype), None),
                    barrier=lambda hdl, channel: dist.barrier())
-    pp = gdist.BucketedGather(shard, **kw_push)
+    pp = gdist.BucketedGather(shard, passes=2, **kw_push)
     check_buckets(pp)
     got_rows, full_rows = pp.exchanged_rows()
     assert 0 <= got_rows <= full_rows
@@ -150,11 +158,21 @@ def _worker(rank, world, port, q, hub=False):
     c = pp.buckets.src_index[pp.buckets.bounds[1]:]
     if c.numel():
         assert int(c.min()) >= 0 and int(c.max()) < nd.recv_offsets[-1] <= nd.buffer_rows
-    for reduce in ["sum", "mean"]:
-        for weighted in (False, True):
-            for _ in range(2):                                          # twice: the buffer is reused across calls
-                got = pp(x_local.clone(), shard.weight if weighted else None, reduce)
-            assert torch.allclose(got, expect(reduce, weighted), rtol=1e-5, atol=1e-6), ("push", reduce, weighted)
+    p1 = gdist.BucketedGather(shard, passes=1, **kw_push)               # single pass: [own rows | needed rows] in one buffer
+    check_buckets(p1)
+    assert p1.exchanged_rows() == pp.exchanged_rows()
+    n_loc = shard.num_local_rows
+    is_remote = (shard.src_index < rb[rank]) | (shard.src_index >= rb[rank + 1])
+    assert torch.equal(p1.buckets.src_index[~is_remote], shard.src_index[~is_remote] - rb[rank])
+    if int(is_remote.sum()):
+        cr = p1.buckets.src_index[is_remote]
+        assert int(cr.min()) >= n_loc and int(cr.max()) < n_loc + p1.needed.recv_offsets[-1] <= p1.needed.buffer_rows
+    for obj in (pp, p1):
+        for reduce in ["sum", "mean"]:
+            for weighted in (False, True):
+                for _ in range(2):                                      # twice: the buffer is reused across calls
+                    got = obj(x_local.clone(), shard.weight if weighted else None, reduce)
+                assert torch.allclose(got, expect(reduce, weighted), rtol=1e-5, atol=1e-6), ("push", obj.passes, reduce, weighted)
     # sparse referencing: when the edges touch few distinct src rows the exchange shrinks accordingly
     few = src_index % 7
     sh2 = gdist.shard_graph(few, dst, None, rank, world, row_bounds=rb, edge_bounds=eb)
@@ -187,7 +205,7 @@ def _worker(rank, world, port, q, hub=False):
     symm.rendezvous = lambda t, group: FakeHandle(t)
     abi.push_rows = fake_push_rows
     try:
-        pd = holder["pd"] = gdist.BucketedGather(shard, transport="push", reducer=reducer)
+        pd = holder["pd"] = gdist.BucketedGather(shard, transport="push", reducer=reducer, passes=2)
         # (a rank with nothing to send skips abi.push_rows on the default path but must still receive in this emulation)
         if pd.needed.send_rows.numel() == 0:
             pd._pusher = pusher

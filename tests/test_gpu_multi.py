@@ -49,9 +49,13 @@ def _worker(rank, world, port, q):
             shard = gdist.shard_graph(src_index.to(dev), dst.to(dev), weight.to(dev).to(dtype), rank, world)
             rb = shard.row_bounds
             x_local = x[rb[rank]:rb[rank + 1]].to(dev)
-            forms = {"allgather": gdist.BucketedGather(shard, transport="allgather"),
-                     "push": gdist.BucketedGather(shard, transport="push")}
+            forms = {"allgather": gdist.BucketedGather(shard, transport="allgather", passes=2),
+                     "push": gdist.BucketedGather(shard, transport="push", passes=2),
+                     "allgather, one pass": gdist.BucketedGather(shard, transport="allgather", passes=1),
+                     "push, one pass": gdist.BucketedGather(shard, transport="push", passes=1)}
+            assert gdist.BucketedGather(shard, transport="allgather").passes in (1, 2)
             got_rows, full_rows = forms["push"].exchanged_rows()
+            assert forms["push, one pass"].exchanged_rows() == (got_rows, full_rows)
             assert got_rows <= full_rows and (gi == 0 or got_rows <= 300)
             tol = 1e-5 if dtype == torch.float32 else 2e-2
             for reduce in ("sum", "mean"):

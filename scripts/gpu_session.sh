@@ -18,6 +18,9 @@ for leg in "$@"; do
   case $leg in
     env:*) export "${leg#env:}";;
     test) timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -25 | tee $OUT/pytest_gpu.txt;;
+    testmulti) timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -x 2>&1 | tail -25 | tee $OUT/pytest_gpu_multi.txt;;
+    benchNown) timeout 900 $TRUN bench.py --gpus $N 2>$OUT/bench_n$N.err | tail -1 > $OUT/bench_n$N.json
+      tail -3 $OUT/bench_n$N.err; cut -c1-400 $OUT/bench_n$N.json;;
     smoke) timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3 | tee $OUT/smoke.txt;;
     bench)
       timeout 900 python bench.py --impl reference 2>$OUT/bench_reference.err | tail -1 > $OUT/bench_reference.json
@@ -27,8 +30,10 @@ for leg in "$@"; do
       timeout 600 $TRUN bench.py --gpus $N --impl reference 2>$OUT/bench_n${N}_reference.err | tail -1 > $OUT/bench_n${N}_reference.json
       timeout 900 $TRUN bench.py --gpus $N 2>$OUT/bench_n$N.err | tail -1 > $OUT/bench_n$N.json
       tail -3 $OUT/bench_n$N.err; cut -c1-600 $OUT/bench_n$N.json;;
-    exch)
-      for wl in reddit_gws products_gs64; do for ex in bucket push allgather replicated; do
+    exch|exch:*)
+      WLS="reddit_gws products_gs64"; EXS="bucket push allgather replicated"
+      if [ "$leg" != exch ]; then IFS=: read -r _ WLS EXS <<< "$leg"; WLS=${WLS//,/ }; EXS=${EXS//,/ }; fi
+      for wl in $WLS; do for ex in $EXS; do
         GEOT_B200_BENCH_SECONDARY=0 GEOT_B200_EXCHANGE=$ex timeout 300 $TRUN bench.py --gpus $N --workload $wl --steps 10 --warmup 3 \
           2>$OUT/exch_${wl}_$ex.err | tail -1 > $OUT/exch_${wl}_$ex.json
         python - <<PY

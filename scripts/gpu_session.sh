@@ -55,6 +55,8 @@ PY
     compare) timeout 900 python scripts/compare_reference_cuda.py > $OUT/compare_reference.jsonl 2> $OUT/compare_reference.err
       timeout 300 python scripts/compare_reference_cuda.py unsorted > $OUT/compare_unsorted.jsonl 2>> $OUT/compare_reference.err
       cut -c1-400 $OUT/compare_reference.jsonl $OUT/compare_unsorted.jsonl; tail -3 $OUT/compare_reference.err;;
+    shards:*) IFS=: read -r _ wl parts <<< "$leg"
+      timeout 300 python scripts/shard_probe.py $wl ${parts:-8} 2>&1 | grep -E "shard|rror" | tee -a $OUT/shard_probe.txt;;
     tune:*) IFS=: read -r _ wl chunks <<< "$leg"
       timeout 300 python scripts/tune.py $wl ${chunks:-0} 2>&1 | grep -E "lib=|rror" | tee -a $OUT/tune.txt;;
     *) echo "unknown leg $leg";;

@@ -306,8 +306,10 @@ class Runner:
                 gdist.all_gather_rows(self.x_local, rb, out=self.x_full)
             if self.exchange in ("bucket", "push"):
                 # passes: 0 = the library's choice (two overlapped passes when the local bucket's rows are long, else one)
+                # phases: 0 = the library's choice (push at >= 6 GPUs: the exchange in two rounds, each followed by its edges)
                 self.bg = gdist.BucketedGather(sh, transport="push" if self.exchange == "push" else "allgather",
-                                               passes=int(os.environ.get("GEOT_B200_EXCHANGE_PASSES", "0")))
+                                               passes=int(os.environ.get("GEOT_B200_EXCHANGE_PASSES", "0")),
+                                               phases=int(os.environ.get("GEOT_B200_EXCHANGE_PHASES", "0")))
                 self.exchanged = self.bg.exchanged_rows()
         else:
             self.di, self.si, self.w, self.S, self.row0 = wk["di"], wk["si"], w, wk["S"], 0
@@ -328,10 +330,19 @@ class Runner:
             self.ws = abi.Workspace(self.E, self.W, wk["dtype"], dev, src_blocks=self.blocks)
         self.n_blocks = self.blocks.n_blocks if self.blocks is not None else 1
         self.passes = self.bg.passes if self.bg is not None else 1
-        self.calls_per_step = self.passes if self.bg is not None else self.n_blocks
-        per_head_perm = 1 if (self.bg is not None and w is not None and w.dim() == 2) else 0
-        # this library's kernels per step: main + fixup per reduction (+ the push kernel, + the per-head weight permutation)
-        self.launches_per_step = 2 * self.calls_per_step + (1 if self.exchange == "push" else 0) + per_head_perm
+        self.phases = self.bg.phases if self.bg is not None else 1
+        self.per_head_perm = 1 if (self.bg is not None and w is not None and w.dim() == 2 and self.passes == 2) else 0
+
+    @property
+    def calls_per_step(self):
+        """Main-kernel launches of one step (known after the first step: a bucket may be src-blocked inside)."""
+        return self.bg.main_launches() if self.bg is not None else self.n_blocks
+
+    @property
+    def launches_per_step(self):
+        """This library's kernels per step: main + fixup per reduction pass (+ one push kernel per exchange round, + the
+        per-head weight permutation)."""
+        return 2 * self.calls_per_step + (self.phases if self.exchange == "push" else 0) + self.per_head_perm
 
     def reduce(self, x, w, out, reduce="sum"):
         """The op on this rank's operands: x = full src (N = 1) / this rank's src rows (N > 1 gather) / edge rows."""
@@ -492,7 +503,8 @@ def summarize(wk, r, ms, kmean, peak, parity, world):
          "edges_per_s": wk["E"] / (ms * 1e-3), "kernel_ms": round(kmean, 4), "kernel_achieved_gbs": round(achieved, 1),
          "frac_of_measured_hbm": round(wk["bytes_logical"] / (ms * 1e-3) / 1e9 / peak, 4),
          "bytes_logical_per_step": wk["bytes_logical"], "bytes_compulsory_per_step": wk["bytes_compulsory"],
-         "traffic": traffic, "exchange": r.exchange, "exchange_passes": r.passes, "src_blocks": r.n_blocks, "parity": parity}
+         "traffic": traffic, "exchange": r.exchange, "exchange_passes": r.passes, "exchange_rounds": r.phases,
+         "main_kernel_launches_per_step": r.calls_per_step, "src_blocks": r.n_blocks, "parity": parity}
     d.update(f)
     return d
 
@@ -670,6 +682,8 @@ def run_own(args):
     if r.bg is not None:
         cfg["exchange_passes"] = ("%d (%s)" % (r.passes, "src-local bucket overlapped with the exchange, src-remote bucket accumulated"
                                                  if r.passes == 2 else "exchange, then one reduction over own + received rows"))
+        cfg["exchange_rounds"] = r.phases
+        cfg["main_kernel_launches_per_step"] = r.calls_per_step
     meta = dict(metric=metric_name(wk), dtype=DTYPE_NAME[wk["dtype"]], config=cfg, E=wk["E"],
                 launches=r.launches_per_step, exchange=r.exchange, imbalance=r.imbalance, exchanged=r.exchanged)
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
     "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_permute_edges",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
-    "geot_b200_push_rows",
+    "geot_b200_push_rows", "geot_b200_push_rows_ex",
     "geot_b200_host_last_transfer", "geot_b200_host_row_pointers", "geot_b200_segment_reduce_ex",
     "geot_b200_host_graph_create", "geot_b200_host_graph_reduce", "geot_b200_host_graph_last_transfer",
     "geot_b200_host_graph_destroy", "geot_b200_src_blocks_suggest", "geot_b200_src_blocks_bytes",
@@ -103,6 +103,7 @@ def lib() -> ctypes.CDLL:
         L.geot_b200_permute_edges.argtypes = [vp, vp, vp, i64, i64, vp]
         L.geot_b200_segment_reduce_host.argtypes = [vp, i64, vp, vp, vp, vp, i64, i64, i64, i64, ci, ci, ci]
         L.geot_b200_push_rows.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, vp]
+        L.geot_b200_push_rows_ex.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, ci, vp]
         L.geot_b200_host_last_transfer.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
         L.geot_b200_host_row_pointers.argtypes = [vp, i64, i64, i64, vp, ci]
         _lib = L
@@ -261,14 +262,14 @@ def permute_edges(x, perm, out=None):
     return out
 
 
-def push_rows(x, rows, dest_peer, dest_row, peer_bases_dev: int, aligned16: bool = True):
-    """peer_bases[dest_peer[e]][dest_row[e]] = x[rows[e]] through geot_b200_push_rows.  ``peer_bases_dev``: device
+def push_rows(x, rows, dest_peer, dest_row, peer_bases_dev: int, aligned16: bool = True, max_ctas: int = 0):
+    """peer_bases[dest_peer[e]][dest_row[e]] = x[rows[e]] through geot_b200_push_rows_ex.  ``peer_bases_dev``: device
     address of the array of per-GPU base pointers (``_SymmetricMemory.buffer_ptrs_dev``, or the ``data_ptr()`` of an
-    int64 device tensor holding the addresses)."""
+    int64 device tensor holding the addresses).  ``max_ctas`` > 0: a small grid for a push that overlaps a reduction."""
     n = rows.numel()
     row_bytes = x[0].numel() * x.element_size() if x.shape[0] else 4
-    check(lib().geot_b200_push_rows(_ptr(x), _ptr(rows), _ptr(dest_peer), _ptr(dest_row), ctypes.c_void_p(peer_bases_dev),
-                                    n, row_bytes, 1 if aligned16 else 0, _stream()), "push_rows")
+    check(lib().geot_b200_push_rows_ex(_ptr(x), _ptr(rows), _ptr(dest_peer), _ptr(dest_row), ctypes.c_void_p(peer_bases_dev),
+                                       n, row_bytes, 1 if aligned16 else 0, max_ctas, _stream()), "push_rows")
 
 
 def host_last_transfer():

@@ -66,10 +66,17 @@ int geot_b200_src_blocks_suggest(int64_t E, int64_t S, int64_t N_src, int64_t ro
   // what the L2 keeps of a read-shared matrix (profiles/r02a_l2probe.txt: 59.6 MB stays, 119 MB does not; two blocks
   // of 68 MB measured best on the proteins shape, profiles/r02a_blocks.txt)
   const double kKeep = 68.0 * 1024 * 1024;
+  const int64_t kMaxUsefulBlocks = 4;
+  const double kMinBlockDegree = 32.0;      // edges per dst row and pass
   const double src_bytes = (double)N_src * (double)row_bytes;
   if (src_bytes <= 64.0 * 1024 * 1024) return 1;             // already resident
   int64_t B = (int64_t)((src_bytes + kKeep - 1) / kKeep);
-  if (B > GEOT_MAX_SRC_BLOCKS) return 1;
+  // only the measured regime: 2 - 4 blocks (profiles/r02a_blocks_*.json), and passes whose rows stay long.  A pass with a
+  // handful of edges per dst row closes a row every few edges and re-reads dst each time: shard 2 of the products shape at
+  // 8 GPUs (40 edges per row, a 627 MB src matrix => 9 blocks of 4.5 edges per row) ran 3.2x SLOWER blocked
+  // (0.74 vs 0.23 ms, profiles/r02h_n8_bench_n8.json vs r02i shard probe); the byte count below does not see that.
+  if (B > kMaxUsefulBlocks) return 1;
+  if ((double)E < kMinBlockDegree * (double)B * (double)S) return 1;
   // re-reads avoided (edges whose row would have missed) against the extra passes over dst, with a 2x margin
   const double saved = (double)E * (1.0 - kKeep / src_bytes);
   const double cost = 2.0 * (double)(B - 1) * (double)S;

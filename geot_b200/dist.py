@@ -184,14 +184,27 @@ class NeededRows:
     buffer_rows: int                 # rows of the (symmetric: same size everywhere) receive buffer
 
 
-def split_local_remote(shard: GraphShard):
-    """(perm [E] int64, n_local): stable split of the shard's edges into src-local first, src-remote second."""
-    rb, rank = shard.row_bounds, shard.rank
+def split_local_remote(shard: GraphShard, phase_steps=None):
+    """(perm [E] int64, bounds): stable split of the shard's edges by where their src row lives -- src-local edges
+    first, then the src-remote ones.  ``phase_steps`` (optional, ascending, last = world-1) cuts the remote edges further
+    by the exchange step that delivers their row (step k = the rows of rank+k): remote group p holds the owners at
+    steps ``(phase_steps[p-1], phase_steps[p]]``.  ``bounds`` = edge offsets of the groups, ``len = groups + 1``."""
+    rb, rank, world = shard.row_bounds, shard.rank, shard.world_size
     s = shard.src_index
-    remote = ((s < rb[rank]) | (s >= rb[rank + 1])).to(torch.int8)
-    perm = torch.argsort(remote, stable=True)
-    n_local = int(s.numel() - int(remote.sum()))
-    return perm, n_local
+    if phase_steps is None or len(phase_steps) <= 1 or world <= 2:
+        key = ((s < rb[rank]) | (s >= rb[rank + 1])).to(torch.int8)
+        groups = 2
+    else:
+        cuts = torch.tensor(rb[1:-1], dtype=s.dtype, device=s.device)
+        step = (torch.bucketize(s, cuts, right=True) - rank) % world            # 0 = local, k = delivered in step k
+        key = torch.bucketize(step, torch.tensor([0] + list(phase_steps[:-1]), dtype=step.dtype, device=s.device), right=False).to(torch.int8)
+        groups = 1 + len(phase_steps)
+    perm = torch.argsort(key, stable=True)
+    counts = torch.bincount(key.long(), minlength=groups).tolist()
+    bounds = [0]
+    for c in counts:
+        bounds.append(bounds[-1] + int(c))
+    return perm, bounds
 
 
 def build_needed_rows(shard: GraphShard, remote_src: torch.Tensor, group=None, own_rows_first: bool = False):
@@ -272,17 +285,18 @@ class BucketedGather:
     Injectable stand-ins (the gloo tests check the host logic on CPU; defaults = the C-ABI kernels, NCCL, torch
     symmetric memory):
       ``reducer(x, src_ids, dst_ids, weight, edge_perm, S, out, accumulate, mean_rowptr, reduce)``
-      ``allocator(shape, dtype, device) -> (buffer, handle)``; ``pusher(x_local, nd, buffer, handle)``;
+      ``allocator(shape, dtype, device) -> (buffer, handle)``; ``pusher(x_local, nd, buffer, handle[, steps=(a, b)])``;
       ``barrier(handle, channel)``."""
 
     # two passes pay when the rows of the local bucket are long enough that closing every dst row twice (and adding
     # into it) costs less than the overlap buys: Reddit-shape shards (61 local edges per row at 8 GPUs) yes,
     # products-shape ones (3) no -- measured at N = 2, profiles/r02g_n2_exch.txt
     MIN_LOCAL_DEGREE = 16
+    PUSH_CTAS = 2 * 148        # grid of a push that runs beside a reduction (geot_b200_push_rows_ex)
 
     def __init__(self, shard: GraphShard, group=None, transport: str = "allgather", reducer=None, allocator=None,
-                 pusher=None, barrier=None, passes: int = 0):
-        assert transport in ("allgather", "push") and passes in (0, 1, 2)
+                 pusher=None, barrier=None, passes: int = 0, phases: int = 0):
+        assert transport in ("allgather", "push") and passes in (0, 1, 2) and phases >= 0
         assert shard.src_index is not None
         self.shard, self.group, self.transport = shard, group, transport
         self.world, self.rank = shard.world_size, shard.rank
@@ -291,7 +305,18 @@ class BucketedGather:
         rb, rank = shard.row_bounds, shard.rank
         E = shard.dst_index.numel()
         assert E < 2 ** 31, "edge_perm is int32"
-        perm, n_local = split_local_remote(shard)
+        # push transport, overlapped form: the exchange may run in `phases` rounds (round p delivers the rows of the owners
+        # at steps (phase_steps[p-1], phase_steps[p]]), each followed by the reduction of the edges it serves, so that only
+        # the first round's transfer is exposed.  Default: 2 rounds from 6 GPUs on (at 8 GPUs a Reddit-shape rank receives
+        # 104 MB per call -- 0.16 ms on the wire against 0.06 ms of src-local work to hide it behind), else 1.
+        if phases == 0:
+            phases = 2 if (transport == "push" and self.world >= 6) else 1
+        if transport != "push" or self.world <= 2:
+            phases = 1
+        phases = min(phases, max(self.world - 1, 1))
+        self.phase_steps = [((self.world - 1) * (p + 1)) // phases for p in range(phases)]      # ascending, last = world-1
+        perm, bounds = split_local_remote(shard, self.phase_steps)
+        n_local = bounds[1]
         if passes == 0:
             # the same choice on every rank (the transports are collective): decided on the total local-src edge count
             t = torch.tensor([float(n_local), float(max(shard.num_local_rows, 1))], dtype=torch.float64, device=shard.dst_index.device)
@@ -299,6 +324,7 @@ class BucketedGather:
                 dist.all_reduce(t, group=group)
             passes = 2 if t[0].item() / t[1].item() >= self.MIN_LOCAL_DEGREE else 1
         self.passes = passes
+        self.phases = phases if passes == 2 else 1
         self.needed = None
         if passes == 1:
             # single pass: the shard's edge list as it is (no permutation), src ids into ONE buffer that holds the own
@@ -310,18 +336,21 @@ class BucketedGather:
                 src[~remote] -= rb[rank]
                 src[remote] = compact
             self.buckets = SrcBuckets(None, [0, E, E], src.contiguous(), shard.dst_index)
+            self.phase_steps = [self.world - 1]
         else:
             src = shard.src_index[perm]
             src[:n_local] -= rb[rank]                      # bucket 0 reads the rank's own rows
             if transport == "push":
                 self.needed, compact = build_needed_rows(shard, src[n_local:].clone(), group)
                 src[n_local:] = compact
-            self.buckets = SrcBuckets(perm.to(torch.int32).contiguous(), [0, n_local, E], src.contiguous(),
+            self.buckets = SrcBuckets(perm.to(torch.int32).contiguous(), bounds, src.contiguous(),
                                       shard.dst_index[perm].contiguous())
         self._plans, self._ws, self._bufs, self._mean_rowptr, self._wperm = {}, {}, {}, None, None
         self._replica = None
-        self.comm_stream = torch.cuda.Stream() if self.cuda else None
-        self.event = torch.cuda.Event() if self.cuda else None
+        # the exchange runs on a HIGH-priority side stream: its small push grid gets the next free SM slots although the
+        # src-local reduction was launched over the whole GPU
+        self.comm_stream = torch.cuda.Stream(priority=-1) if self.cuda else None
+        self.events = [torch.cuda.Event() for _ in range(self.phases)] if self.cuda else None
 
     # -- per-graph facts ------------------------------------------------------------------------------
     def exchanged_rows(self):
@@ -329,6 +358,18 @@ class BucketedGather:
         rb = self.shard.row_bounds
         full = rb[-1] - (rb[self.rank + 1] - rb[self.rank])
         return (self.needed.recv_offsets[-1] if self.needed is not None else full), full
+
+    def main_launches(self) -> int:
+        """Reduction launches of one call as set up so far (a bucket that is src-blocked for the L2 takes one per block;
+        known after the first call at a given row width)."""
+        b = self.buckets.bounds
+        n = 0
+        for k in range(len(b) - 1):
+            if b[k + 1] == b[k]:
+                continue
+            blocks = [v[1] for key, v in self._ws.items() if key[0] == k]
+            n += blocks[-1].n_blocks if (blocks and blocks[-1] is not None) else 1
+        return n
 
     def local_rows(self, x_full: torch.Tensor) -> torch.Tensor:
         rb = self.shard.row_bounds
@@ -370,7 +411,7 @@ class BucketedGather:
             blocks = None
             nb = 1
             if H == 1 and self.cuda and x.element_size() >= 4:         # (16-bit outputs would be rounded once per pass)
-                nb = abi.src_blocks_suggest(e1 - e0, S, x.shape[0], W * x.element_size())
+                nb = abi.src_blocks_suggest(e1 - e0, S, self._rows_touched(k, x.shape[0]), W * x.element_size())
             if nb > 1:
                 blocks = abi.SrcBlocks(si, di, x.shape[0], nb)
                 if perm is not None:
@@ -385,6 +426,26 @@ class BucketedGather:
         abi.segment_reduce(x, si, di, weight, reduce, S=S, H=H, plan=self._plans[k], out=out, workspace=ws,
                            accumulate=accumulate, edge_perm=perm if weight is not None else None,
                            mean_rowptr=mean_rowptr if self.passes == 2 else None)
+
+    def _rows_touched(self, k, n_rows):
+        """Rows of its operand that bucket k can gather from (its working set for the L2): a remote bucket of the push
+        transport reads only the rows its exchange round delivered."""
+        if k == 0 or self.needed is None or self.passes == 1:
+            return n_rows
+        lo, hi = self._phase_rows(k - 1)
+        return max(hi - lo, 1)
+
+    def _phase_rows(self, p):
+        """[lo, hi) rows of the receive buffer that exchange round p delivers."""
+        st = [0] + self.phase_steps
+        off = self.needed.recv_offsets
+        return off[st[p]], off[st[p + 1]]
+
+    def _phase_sends(self, p):
+        """[lo, hi) of the send list that exchange round p pushes (the list is grouped by peer in step order)."""
+        st = [0] + self.phase_steps
+        cnt = [self.needed.send_counts[(self.rank - k) % self.world] for k in range(1, self.world)]
+        return sum(cnt[:st[p]]), sum(cnt[:st[p + 1]])
 
     def _bucket_order(self, weight):
         """Per-head weights [E, H] in bucket order (one permutation pass per call: the kernel's edge_perm serves one
@@ -424,20 +485,35 @@ class BucketedGather:
                 self._bufs[key] = (buf, _PeerBuffer(hdl, bases))
         return self._bufs[key]
 
-    def _exchange(self, x_local, buf, hdl):
+    def _exchange(self, x_local, buf, hdl, events=None):
+        """The src-row exchange on the current stream.  ``events`` (overlapped push form): one per exchange round, recorded
+        when that round's rows have landed."""
         if self.transport == "allgather":
             all_gather_rows(x_local, self.shard.row_bounds, self.group, out=buf)
+            if events is not None:
+                events[0].record()
             return
         nd = self.needed
         if self.passes == 1 and x_local.shape[0]:
             buf[: x_local.shape[0]].copy_(x_local)          # the buffer starts with the rank's own rows
         self._barrier(hdl, 0)              # every peer is done reading its receive buffer (its previous call)
-        if self._pusher is not None:       # (a stand-in also plays the receiving side: runs even with nothing to send)
-            self._pusher(x_local, nd, buf, hdl)
-        elif nd.send_rows.numel():
-            from . import abi
-            abi.push_rows(x_local, nd.send_rows, nd.dest_peer, nd.dest_row, hdl.bases.data_ptr())
-        self._barrier(hdl, 1)              # every peer's rows are in my buffer
+        for p in range(self.phases):
+            if self._pusher is not None:   # (a stand-in also plays the receiving side: runs even with nothing to send)
+                if self.phases == 1:
+                    self._pusher(x_local, nd, buf, hdl)
+                else:                      # round p = exchange steps (a, b]: to ranks rank-k, from ranks rank+k
+                    st = [0] + self.phase_steps
+                    self._pusher(x_local, nd, buf, hdl, steps=(st[p], st[p + 1]))
+            else:
+                lo, hi = self._phase_sends(p) if self.phases > 1 else (0, nd.send_rows.numel())
+                if hi > lo:
+                    from . import abi
+                    # overlapped form: a small grid (2 CTAs per SM) that shares the SMs with the running reduction
+                    abi.push_rows(x_local, nd.send_rows[lo:hi], nd.dest_peer[lo:hi], nd.dest_row[lo:hi], hdl.bases.data_ptr(),
+                                  max_ctas=self.PUSH_CTAS if self.passes == 2 else 0)
+            self._barrier(hdl, 1)          # every peer's rows of this round are in my buffer
+            if events is not None:
+                events[p].record()
 
     def _barrier(self, hdl, channel):
         if self._barrier_fn is not None:
@@ -463,16 +539,16 @@ class BucketedGather:
         if self.cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream())   # x_local is final; buf's old rows were consumed
             with torch.cuda.stream(self.comm_stream):
-                self._exchange(x_local, buf, hdl)
-                self.event.record(self.comm_stream)
+                self._exchange(x_local, buf, hdl, self.events)
         else:
             self._exchange(x_local, buf, hdl)
         if weight is not None and weight.dim() == 2 and self._reducer is None:
             weight = self._bucket_order(weight)
         self._reduce_bucket(0, x_local, weight, out, reduce, accumulate=False)
-        if self.cuda:
-            torch.cuda.current_stream().wait_event(self.event)
-        self._reduce_bucket(1, buf, weight, out, reduce, accumulate=True)
+        for p in range(self.phases):       # the edges served by exchange round p, as soon as its rows have landed
+            if self.cuda:
+                torch.cuda.current_stream().wait_event(self.events[p])
+            self._reduce_bucket(1 + p, buf, weight, out, reduce, accumulate=True)
         return out
 
     def aggregate(self, x_local: torch.Tensor, weight: Optional[torch.Tensor] = None, reduce: str = "sum") -> torch.Tensor:

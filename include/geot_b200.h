@@ -243,6 +243,12 @@ GEOT_API int geot_b200_permute_edges(const void *in, const int64_t *perm, void *
 GEOT_API int geot_b200_push_rows(const void *x, const int64_t *rows, const int32_t *dest_peer, const int64_t *dest_row,
                         void *const *peer_bases, int64_t n, int64_t row_bytes, int peers_aligned16,
                         cudaStream_t stream);
+/* The same transfer on a grid of at most max_ctas CTAs (128 threads, <= 48 registers each), for a push that runs BESIDE
+ * a reduction on another stream: 2 CTAs per SM (296) keep an NVLink direction ~85 % busy and still fit next to the
+ * resident CTAs of the reduction kernel.  max_ctas <= 0: the whole GPU (= geot_b200_push_rows). */
+GEOT_API int geot_b200_push_rows_ex(const void *x, const int64_t *rows, const int32_t *dest_peer, const int64_t *dest_row,
+                           void *const *peer_bases, int64_t n, int64_t row_bytes, int peers_aligned16, int max_ctas,
+                           cudaStream_t stream);
 
 /* ---- host-buffer entry (end-to-end path) ----------------------------------------------------- */
 

@@ -5,7 +5,7 @@
 # legs: test (pytest -m gpu) | smoke | bench (default bench.py, own + reference arm) | benchN (torchrun bench at N = all
 #       visible GPUs, own + reference arm) | exch (N > 1: products / reddit with every exchange form) | model (configs[4]
 #       at N GPUs) | launches (ncu launch list of the default bench) | ncu:<workload> (one --set full capture) |
-#       tune:<workload>[:chunks] | compare (the reference's own CUDA kernels beside ours, sorted and sorted=False) |
+#       tune:<workload>[:chunks] | timeline:<workload>[:exchange] (N > 1: where the step goes, CUDA-graph replay) | compare (the reference's own CUDA kernels beside ours, sorted and sorted=False) |
 #       env:<NAME=VALUE> (exported for the legs that follow)
 TAG=$1; shift
 OUT=gpurun_out/$TAG
@@ -49,12 +49,15 @@ PY
     launches)
       GEOT_B200_BENCH_SECONDARY=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
         python bench.py --steps 3 --warmup 3 > $OUT/bench_under_ncu.log 2>&1; grep -c geot $OUT/launches.csv;;
-    ncu:*) wl=${leg#ncu:}
-      GEOT_B200_BENCH_SECONDARY=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:segment_reduce_kernel -s 3 -c 1 -o $OUT/prof_$wl \
+    ncu:*) IFS=: read -r _ wl cnt <<< "$leg"; cnt=${cnt:-1}      # cnt = main-kernel launches of one step (src blocks)
+      GEOT_B200_BENCH_SECONDARY=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:segment_reduce_kernel -s $((3 * cnt)) -c $cnt -o $OUT/prof_$wl \
         python bench.py --workload $wl --steps 3 --warmup 3 > $OUT/prof_$wl.log 2>&1; ls -la $OUT/prof_$wl.ncu-rep;;
     compare) timeout 900 python scripts/compare_reference_cuda.py > $OUT/compare_reference.jsonl 2> $OUT/compare_reference.err
       timeout 300 python scripts/compare_reference_cuda.py unsorted > $OUT/compare_unsorted.jsonl 2>> $OUT/compare_reference.err
       cut -c1-400 $OUT/compare_reference.jsonl $OUT/compare_unsorted.jsonl; tail -3 $OUT/compare_reference.err;;
+    timeline:*) IFS=: read -r _ wl ex <<< "$leg"
+      timeout 300 $TRUN scripts/exchange_timeline.py $wl ${ex:-push} 2>$OUT/timeline_${wl}_${ex:-push}.err | grep -E "N=|rows pushed|rounds|graph|rror" | tee -a $OUT/timeline.txt
+      tail -2 $OUT/timeline_${wl}_${ex:-push}.err;;
     shards:*) IFS=: read -r _ wl parts <<< "$leg"
       timeout 300 python scripts/shard_probe.py $wl ${parts:-8} 2>&1 | grep -E "shard|rror" | tee -a $OUT/shard_probe.txt;;
     tune:*) IFS=: read -r _ wl chunks <<< "$leg"

@@ -81,6 +81,7 @@ def report_md(tag, name, rep, dst, traffic):
     if len(rows) < 3:
         return
     hdr, units = rows[0], rows[1]
+    seen = 0
     with open(dst, "w") as f:
         f.write("# %s: `ncu --set full --clock-control none --import-source on` capture `%s`\n\n" % (tag, name))
         for r in rows[2:]:
@@ -99,8 +100,14 @@ def report_md(tag, name, rep, dst, traffic):
             try:
                 rd = float(d["dram__bytes_read.sum"][0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_read.sum"][1]]
                 wr = float(d["dram__bytes_write.sum"][0]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[d["dram__bytes_write.sum"][1]]
-                traffic[name] = {"kernel": d["Kernel Name"][0], "dram_bytes_per_launch": int(rd + wr),
-                                 "dram_read": int(rd), "dram_write": int(wr), "source": "profiles/%s_%s.md" % (tag, name)}
+                # a capture holds the main-kernel launches of ONE step (one per src block): their bytes add up
+                t = traffic.get(name) if seen else None
+                seen += 1
+                traffic[name] = {"kernel": d["Kernel Name"][0], "launches": seen,
+                                 "dram_bytes_per_launch": int(rd + wr) + (t["dram_bytes_per_launch"] if t else 0),
+                                 "dram_read": int(rd) + (t["dram_read"] if t else 0),
+                                 "dram_write": int(wr) + (t["dram_write"] if t else 0),
+                                 "source": "profiles/%s_%s.md" % (tag, name)}
             except Exception:
                 pass
         # hottest source lines (needs -lineinfo)

@@ -266,4 +266,9 @@ def test_src_blocks_suggestion_rule():
     assert abi.src_blocks_suggest(114_615_892, 232_965, 232_965, 256) == 1        # 60 MB: already resident
     assert abi.src_blocks_suggest(61_859_140, 2_449_029, 2_449_029, 256) == 1     # products: degree 25, no reuse to save
     assert abi.src_blocks_suggest(1_166_243, 169_343, 169_343, 512) == 1          # arxiv
+    # dst-row shards keep the rule's verdict: a Reddit-shape shard of 8 still blocks, the hub shard of the products shape
+    # (40 edges per row against a 627 MB matrix: 9 passes of 4.5 edges per row, measured 3.2x slower) does not
+    assert abi.src_blocks_suggest(14_327_639, 28_837, 232_965, 512) == 2
+    assert abi.src_blocks_suggest(8_203_841, 201_546, 2_449_029, 256) == 1
+    assert abi.src_blocks_suggest(400_000_000, 232_965, 2_000_000, 512) == 1      # 15 blocks: outside the measured regime
     assert abi.src_blocks_suggest(0, 1, 1, 4) == 1

@@ -91,14 +91,21 @@ def _worker(rank, world, port, q, hub=False):
             assert b.perm is None and b.bounds == [0, shard.num_local_edges, shard.num_local_edges]
             assert torch.equal(b.dst_index, shard.dst_index)
             return
-        assert b.bounds[0] == 0 and b.bounds[2] == shard.num_local_edges and b.perm.dtype == torch.int32
+        assert b.bounds[0] == 0 and b.bounds[-1] == shard.num_local_edges and b.perm.dtype == torch.int32
+        assert len(b.bounds) == 2 + bg.phases and b.bounds == sorted(b.bounds)
         glob = shard.src_index[b.perm.long()]
         loc = (glob >= rb[rank]) & (glob < rb[rank + 1])
         assert bool(loc[: b.bounds[1]].all()) and not bool(loc[b.bounds[1]:].any())
         assert torch.equal(b.src_index[: b.bounds[1]], glob[: b.bounds[1]] - rb[rank])
-        for k in range(2):
+        cuts = torch.tensor(rb[1:-1], dtype=torch.int64)
+        step = (torch.bucketize(glob, cuts, right=True) - rank) % world  # exchange step that delivers the edge's row
+        st = [0] + bg.phase_steps
+        for k in range(len(b.bounds) - 1):
             d_k = b.dst_index[b.bounds[k]:b.bounds[k + 1]]
             assert bool((d_k[1:] >= d_k[:-1]).all())                   # stable split keeps dst order
+            if k >= 1:                                                  # remote group k-1 = the owners of its exchange round
+                s_k = step[b.bounds[k]:b.bounds[k + 1]]
+                assert bool(((s_k > st[k - 1]) & (s_k <= st[k])).all())
 
     def expect(reduce, weighted):
         full = (oracle.gather_weight_scatter(src_index, dst, weight, x, reduce) if weighted
@@ -124,16 +131,19 @@ def _worker(rank, world, port, q, hub=False):
     # (dest_peer / dest_row) and the compact src ids are what is under test.
     holder = {}
 
-    def pusher(x_mine, nd, buf, hdl):
+    def pusher(x_mine, nd, buf, hdl, steps=None):
         ops, inbox = [], {}
+        a, b = steps if steps is not None else (0, world - 1)          # exchange steps (a, b] of this round
         for p in range(world):
             if p == rank:
                 continue
             m = nd.dest_peer == p
+            if not (a < (rank - p) % world <= b):                       # I serve rank-k in step k
+                m = m & False
             if int(m.sum()):
                 ops.append(dist.P2POp(dist.isend, nd.dest_row[m].contiguous(), p, tag=1))
                 ops.append(dist.P2POp(dist.isend, x_mine[nd.send_rows[m]].contiguous(), p, tag=2))
-            n = nd.recv_counts[p]
+            n = nd.recv_counts[p] if (a < (p - rank) % world <= b) else 0   # rank+k's rows arrive in step k
             if n:
                 inbox[p] = (torch.empty(n, dtype=torch.int64), torch.empty([n] + list(x_mine.shape[1:]), dtype=x_mine.dtype))
                 ops.append(dist.P2POp(dist.irecv, inbox[p][0], p, tag=1))
@@ -158,6 +168,24 @@ def _worker(rank, world, port, q, hub=False):
     c = pp.buckets.src_index[pp.buckets.bounds[1]:]
     if c.numel():
         assert int(c.min()) >= 0 and int(c.max()) < nd.recv_offsets[-1] <= nd.buffer_rows
+    # the exchange in rounds: every round's rows land in their own range of the buffer and serve their own edge group
+    for phases in (1, 2, 3):
+        pk = gdist.BucketedGather(shard, passes=2, phases=phases, **kw_push)
+        assert pk.phases == (1 if world <= 2 else min(phases, world - 1)) and pk.phase_steps[-1] == world - 1
+        check_buckets(pk)
+        assert pk.exchanged_rows() == pp.exchanged_rows()
+        sends = [pk._phase_sends(p) for p in range(pk.phases)]
+        rows = [pk._phase_rows(p) for p in range(pk.phases)]
+        assert sends[0][0] == 0 and sends[-1][1] == pk.needed.send_rows.numel() and rows[0][0] == 0 and rows[-1][1] == pk.needed.recv_offsets[-1]
+        assert all(sends[i][1] == sends[i + 1][0] and rows[i][1] == rows[i + 1][0] for i in range(pk.phases - 1))
+        for k in range(1, pk.phases + 1):                               # a remote group reads only its round's rows
+            c_k = pk.buckets.src_index[pk.buckets.bounds[k]:pk.buckets.bounds[k + 1]]
+            if c_k.numel():
+                assert rows[k - 1][0] <= int(c_k.min()) and int(c_k.max()) < rows[k - 1][1]
+        for reduce, weighted in (("sum", True), ("mean", False)):
+            for _ in range(2):
+                got = pk(x_local.clone(), shard.weight if weighted else None, reduce)
+            assert torch.allclose(got, expect(reduce, weighted), rtol=1e-5, atol=1e-6), ("push rounds", phases, reduce, weighted)
     p1 = gdist.BucketedGather(shard, passes=1, **kw_push)               # single pass: [own rows | needed rows] in one buffer
     check_buckets(p1)
     assert p1.exchanged_rows() == pp.exchanged_rows()
@@ -196,7 +224,7 @@ def _worker(rank, world, port, q, hub=False):
         def barrier(self, channel=0):
             dist.barrier()
 
-    def fake_push_rows(x_mine, rows, dest_peer, dest_row, bases_ptr, aligned16=True):
+    def fake_push_rows(x_mine, rows, dest_peer, dest_row, bases_ptr, aligned16=True, max_ctas=0):
         h = [h for h in FakeHandle.live if list(h.buf.shape[1:]) == list(x_mine.shape[1:]) and h.buf.dtype == x_mine.dtype][-1]
         pusher(x_mine, holder["pd"].needed, h.buf, None)
 
@@ -205,7 +233,7 @@ def _worker(rank, world, port, q, hub=False):
     symm.rendezvous = lambda t, group: FakeHandle(t)
     abi.push_rows = fake_push_rows
     try:
-        pd = holder["pd"] = gdist.BucketedGather(shard, transport="push", reducer=reducer, passes=2)
+        pd = holder["pd"] = gdist.BucketedGather(shard, transport="push", reducer=reducer, passes=2, phases=1)
         # (a rank with nothing to send skips abi.push_rows on the default path but must still receive in this emulation)
         if pd.needed.send_rows.numel() == 0:
             pd._pusher = pusher

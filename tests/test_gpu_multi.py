@@ -50,10 +50,12 @@ def _worker(rank, world, port, q):
             rb = shard.row_bounds
             x_local = x[rb[rank]:rb[rank + 1]].to(dev)
             forms = {"allgather": gdist.BucketedGather(shard, transport="allgather", passes=2),
-                     "push": gdist.BucketedGather(shard, transport="push", passes=2),
+                     "push": gdist.BucketedGather(shard, transport="push", passes=2, phases=1),
+                     "push, exchange in rounds": gdist.BucketedGather(shard, transport="push", passes=2, phases=world - 1),
                      "allgather, one pass": gdist.BucketedGather(shard, transport="allgather", passes=1),
                      "push, one pass": gdist.BucketedGather(shard, transport="push", passes=1)}
             assert gdist.BucketedGather(shard, transport="allgather").passes in (1, 2)
+            assert forms["push, exchange in rounds"].phases == max(world - 1, 1) if world > 2 else 1
             got_rows, full_rows = forms["push"].exchanged_rows()
             assert forms["push, one pass"].exchanged_rows() == (got_rows, full_rows)
             assert got_rows <= full_rows and (gi == 0 or got_rows <= 300)

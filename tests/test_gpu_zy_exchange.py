@@ -56,9 +56,10 @@ def test_debug_mode_checks_src_index_range(monkeypatch):
         geot_b200.gather_weight_scatter(bad - 11, di, torch.rand(4, device=DEV), x)
 
 
+@pytest.mark.parametrize("max_ctas", [0, 3])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("width", [2, 3, 6, 8, 64, 128, 130])
-def test_push_rows_into_peer_buffers(dtype, width):
+def test_push_rows_into_peer_buffers(dtype, width, max_ctas):
     """geot_b200_push_rows on one GPU: the "peers" are three local buffers whose base pointers sit in a device array,
     exactly as symmetric memory presents the mapped buffers of the other GPUs.  Byte moves: bit-exact."""
     g = torch.Generator().manual_seed(width)
@@ -72,7 +73,8 @@ def test_push_rows_into_peer_buffers(dtype, width):
         slot[m] = torch.randperm(int(m.sum()) + 5, generator=g)[: int(m.sum())]
     bufs = [torch.full((int((peer == p).sum()) + 5, width), -1.0, dtype=dtype, device=DEV) for p in range(3)]
     bases = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
-    abi.push_rows(x, rows.to(DEV), peer.to(DEV), slot.to(DEV), bases.data_ptr(), aligned16=True)
+    # max_ctas = 3: the small persistent grid of the overlapped form (every thread loops over several unrolled batches)
+    abi.push_rows(x, rows.to(DEV), peer.to(DEV), slot.to(DEV), bases.data_ptr(), aligned16=True, max_ctas=max_ctas)
     torch.cuda.synchronize()
     for p in range(3):
         exp = torch.full(bufs[p].shape, -1.0, dtype=dtype)

@@ -47,38 +47,9 @@ int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-// CTAs of the lean-ring kernel that fit one SM (a run-time mirror of ShapeOf<...>::smem_bytes / min_blocks in
-// segment_reduce.cuh, pinned to it by the static_asserts below): sizes the grid in whole waves.
-constexpr int lean_depth_rt(int want, int sb) {
-  int d = want < sb ? want : sb - 1;
-  while (d > 0 && sb % (d + 1) != 0) --d;
-  return d;
-}
-constexpr size_t lean_smem_bytes(int esize, int vecw, int lpr, int vpl, int want_depth, bool headw) {
-  const int ng = geot::kThreads / lpr, cw = lpr * vpl * vecw;
-  const int lu = (vpl >= 4) ? 1 : (vpl == 2 ? 2 : (lpr >= 16 ? 4 : (lpr >= 8 ? 2 : 1)));
-  const int u = lpr < lu ? lpr : lu;
-  const int ns = lean_depth_rt(want_depth, lpr / u) + 1;
-  const size_t carry = (((size_t)ng * cw * 4 + (size_t)ng * (4 * 8 + 4)) + 127) & ~(size_t)127;
-  const size_t ops = (size_t)ng * (headw ? (2 * lpr + 2 * geot::kHeadMax * lpr) : 4 * lpr) * 4;
-  return carry + ops + (size_t)ng * ns * u * cw * esize;
-}
-constexpr int lean_resident_ctas(int esize, int vecw, int lpr, int vpl, int want_depth, bool headw) {
-  const int by_smem = (int)((227 * 1024) / (lean_smem_bytes(esize, vecw, lpr, vpl, want_depth, headw) + 1024));
-  return by_smem >= 3 ? 3 : (by_smem >= 1 ? by_smem : 1);       // __launch_bounds__(256, min_blocks <= 3)
-}
-static_assert(lean_smem_bytes(4, 4, 32, 1, 3, false) == geot::ShapeOf<float, 4, 32, 1, geot::kLeanFlag | 3>::smem_bytes, "mirror");
-static_assert(lean_smem_bytes(4, 4, 32, 1, 7, false) == geot::ShapeOf<float, 4, 32, 1, geot::kLeanFlag | 7>::smem_bytes, "mirror");
-static_assert(lean_smem_bytes(4, 4, 16, 1, 7, false) == geot::ShapeOf<float, 4, 16, 1, geot::kLeanFlag | 3>::smem_bytes, "mirror");
-static_assert(lean_smem_bytes(4, 4, 32, 4, 3, false) == geot::ShapeOf<float, 4, 32, 4, geot::kLeanFlag | 3>::smem_bytes, "mirror");
-static_assert(lean_smem_bytes(2, 8, 32, 1, 3, true) ==
-              geot::ShapeOf<__nv_bfloat16, 8, 32, 1, geot::kLeanFlag | geot::kHeadFlag | 3>::smem_bytes, "mirror");
-static_assert(lean_resident_ctas(4, 4, 32, 1, 3, false) == geot::ShapeOf<float, 4, 32, 1, geot::kLeanFlag | 3>::min_blocks, "mirror");
-static_assert(lean_resident_ctas(4, 4, 32, 1, 7, false) == geot::ShapeOf<float, 4, 32, 1, geot::kLeanFlag | 7>::min_blocks, "mirror");
-
 // `vector_ok`: rows are 16-byte addressable (per-head width multiple of the vector width and
 // 16-byte aligned base pointers); otherwise the element-wise kernels are used.
-Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok, bool gather = true, int per_head = -1) {
+Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok, bool gather = true) {
   Config c;
   const int full = (int)(16 / dtype_size(dtype));
   const int vecw = (vector_ok && F % full == 0) ? full : 1;
@@ -115,21 +86,10 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok,
     // mh_spmm 0.198 ms at chunk 32 -> 0.171 at 128; config #1 index_scatter 0.070 at 256 -> 0.064 at 64)
     while (chunk > 8 && (E + (int64_t)ng * chunk - 1) / ((int64_t)ng * chunk) < 4 * 148) chunk >>= 1;
   }
-  // Whole waves: the grid runs `resident` CTAs per SM at a time and every tile costs the same, so a last wave that is a
-  // quarter full costs a whole wave (a products-shape shard of 8: 1888 tiles = 4.25 waves of 444).  When the grid is
-  // only a few waves deep, shrink the chunk (to a multiple of the group width) until the tiles fill `waves` whole waves.
-  // GEOT_B200_WAVES=0 switches the rule off (A/B).
-  if (env_int("GEOT_B200_CHUNK", 0) <= 0 && env_int("GEOT_B200_WAVES", 1) != 0 && (c.shape.pf & geot::kLeanFlag)) {
-    const int64_t wave = 148LL * lean_resident_ctas((int)dtype_size(dtype), vecw, lpr, vpl, c.shape.pf & geot::kDepthMask,
-                                                    /*headw=*/per_head < 0 ? W != F : per_head != 0);
-    const int64_t tiles = (E + (int64_t)ng * chunk - 1) / ((int64_t)ng * chunk);
-    const int64_t waves = (tiles + wave - 1) / wave;
-    if (waves <= 12 && tiles > wave / 2) {
-      int64_t per_group = (E + waves * wave * ng - 1) / (waves * wave * ng);
-      per_group = (per_group + lpr - 1) / lpr * lpr;
-      if (per_group >= lpr && per_group < chunk) chunk = (int)per_group;
-    }
-  }
+  // (Sizing the grid in whole waves of resident CTAs -- shrinking the chunk until the tiles fill an integer number of
+  // waves -- was measured on the shapes that are only a few waves deep and changed nothing: config #1 0.065 / 0.066 ms,
+  // arxiv mh_spmm 0.138 / 0.138, the 8 products-shape shards 0.220-0.262 / 0.221-0.257, profiles/r02l_tune.txt,
+  // r02l_shard_probe.txt.  The tiles are short enough for the block scheduler to even out the last wave.  Removed.)
   c.chunk_edges = chunk;
   c.tile_edges = (int64_t)ng * chunk;
   c.n_tiles = (E + c.tile_edges - 1) / c.tile_edges;
@@ -420,8 +380,8 @@ size_t geot_b200_workspace_bytes(int64_t E, int64_t W, int dtype, int sorted) {
   if (E <= 0 || W <= 0) return 256;
   // the vector and the element-wise shapes partition differently: size for the larger
   size_t best = 0;
-  for (int v = 0; v < 8; ++v) {       // (and gathers / index_scatter / per-head weights size their waves apart)
-    const Config c = choose_config(E, W, W, dtype, (v & 1) == 1, (v & 2) == 0, (v & 4) ? 1 : 0);
+  for (int v = 0; v < 2; ++v) {
+    const Config c = choose_config(E, W, W, dtype, v == 1);
     Workspace w = carve(nullptr, c.n_tiles, W, dtype);
     best = std::max(best, w.bytes);
   }

@@ -871,6 +871,7 @@ segment_fixup_kernel(const __grid_constant__ Params p) {
   __shared__ int64_t s_last[NW];
   __shared__ int s_is_long[NW];
   __shared__ A s_part[NW * 32];
+  __shared__ __align__(16) float s_part4[sizeof(A) == 4 ? kThreads * 4 : 4];   // long chains, fp32 carries: one float4 per thread
 
   const int64_t t = (int64_t)blockIdx.x * NW + warp;
   const bool has = (t < p.n_tiles) && (p.flags[t] & FLAG_TAIL);
@@ -918,6 +919,67 @@ segment_fixup_kernel(const __grid_constant__ Params p) {
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     n += p.tail_cnt[tt];
     if (p.mean && p.mean_rowptr != nullptr) n = p.mean_rowptr[p.tail_row[tt] + 1] - p.mean_rowptr[p.tail_row[tt]];
+    if constexpr (sizeof(A) == 4) {
+      // fp32 carries in whole 16-byte vectors: VT threads across a carry row, 256 / VT tiles side by side, 8 vector loads
+      // in flight per thread (a products-shape shard whose hub row is cut by 741 tiles: 32 -> 9 us; the chain used to be
+      // walked one 32-column block at a time with 4 scalar loads in flight).  Fixed order: per-lane partial sums over
+      // tiles tl, tl + TL, ..., then the TL partials left to right, then the tail carry.
+      if ((W & 3) == 0) {
+        const int nvec = (int)(W >> 2);
+        int VT = 1;
+        while (VT < nvec && VT < kThreads) VT <<= 1;
+        const int TL = kThreads / VT;
+        const int v = threadIdx.x % VT, tl = threadIdx.x / VT;
+        float4 *s_vec = reinterpret_cast<float4 *>(s_part4);
+        for (int v0 = 0; v0 < nvec; v0 += VT) {
+          const int vv = v0 + v;
+          float4 a = make_float4(red_identity<RED, float>(), red_identity<RED, float>(), red_identity<RED, float>(),
+                                 red_identity<RED, float>());
+          if (vv < nvec) {
+            const float4 *hv = reinterpret_cast<const float4 *>(head) + vv;
+            const int64_t rowv = W >> 2;
+            int64_t j = tt + 1 + tl;
+            constexpr int UN = 8;
+            for (; j + (int64_t)(UN - 1) * TL <= lst; j += (int64_t)UN * TL) {
+              float4 x[UN];
+#pragma unroll
+              for (int u = 0; u < UN; ++u) x[u] = __ldcg(hv + (j + (int64_t)u * TL) * rowv);
+#pragma unroll
+              for (int u = 0; u < UN; ++u) {
+                a.x = red_op<RED, float>(a.x, x[u].x); a.y = red_op<RED, float>(a.y, x[u].y);
+                a.z = red_op<RED, float>(a.z, x[u].z); a.w = red_op<RED, float>(a.w, x[u].w);
+              }
+            }
+            for (; j <= lst; j += TL) {
+              const float4 x = __ldcg(hv + j * rowv);
+              a.x = red_op<RED, float>(a.x, x.x); a.y = red_op<RED, float>(a.y, x.y);
+              a.z = red_op<RED, float>(a.z, x.z); a.w = red_op<RED, float>(a.w, x.w);
+            }
+          }
+          s_vec[tl * VT + v] = a;
+          __syncthreads();
+          if (tl == 0 && vv < nvec) {
+            const float4 t4 = reinterpret_cast<const float4 *>(static_cast<const float *>(p.carry_tail) + tt * W)[vv];
+            float r[4] = {t4.x, t4.y, t4.z, t4.w};
+            for (int k = 0; k < TL; ++k) {
+              const float4 q = s_vec[k * VT + v];
+              r[0] = red_op<RED, float>(r[0], q.x); r[1] = red_op<RED, float>(r[1], q.y);
+              r[2] = red_op<RED, float>(r[2], q.z); r[3] = red_op<RED, float>(r[3], q.w);
+            }
+            T *q = static_cast<T *>(p.dst) + p.tail_row[tt] * W + (int64_t)vv * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float o = r[i];
+              if (p.mean) o = o / static_cast<float>(n);
+              if (p.accumulate) o = to_acc<T>(q[i]) + o;
+              q[i] = from_acc<T>(o);
+            }
+          }
+          __syncthreads();
+        }
+        continue;
+      }
+    }
     for (int64_t c0 = 0; c0 < W; c0 += 32) {
       const int64_t c = c0 + lane;
       A a = red_identity<RED, A>();

@@ -114,7 +114,7 @@ def unsorted():
     for (E, S, F) in [(1_000_000, 50_000, 64), (10_000_000, 200_000, 64), (1_000_000, 50_000, 128)]:
         g = torch.Generator(device="cuda").manual_seed(0)
         idx = torch.randint(0, S, (E,), generator=g, device="cuda")
-        idx[0] = S - 1
+        idx[-1] = S - 1           # the reference sizes its output from index[-1] + 1 (csrc/index_scatter.cpp:30-34)
         x = torch.rand(E, F, generator=g, device="cuda")
         ours = lambda: geot_b200.index_scatter(0, x, idx, "sum", False)
         rec = {"workload": "index_scatter sorted=False, random index", "E": E, "S": S, "F": F, "dtype": "f32"}
@@ -130,6 +130,7 @@ def unsorted():
             rec["reference_cuda_atomic_kernel_ms"] = {"best": round(rb, 4), "median": round(rm, 4)}
             rec["speedup_vs_reference"] = round(rb / b, 2)
             a, r = ours(), ref()
+            assert a.shape == r.shape, (a.shape, r.shape)
             rec["max_rel_diff_vs_reference"] = float(((a - r).abs() / r.abs().clamp_min(1e-30)).max())
             rec["ours_bit_reproducible"] = bool(torch.equal(a, ours()))
             rec["reference_bit_reproducible"] = bool(torch.equal(r, ref()))

@@ -5,7 +5,8 @@
 # legs: test (pytest -m gpu) | smoke | bench (default bench.py, own + reference arm) | benchN (torchrun bench at N = all
 #       visible GPUs, own + reference arm) | exch (N > 1: products / reddit with every exchange form) | model (configs[4]
 #       at N GPUs) | launches (ncu launch list of the default bench) | ncu:<workload> (one --set full capture) |
-#       tune:<workload>[:chunks] | timeline:<workload>[:exchange] (N > 1: where the step goes, CUDA-graph replay) | compare (the reference's own CUDA kernels beside ours, sorted and sorted=False) |
+#       tune:<workload>[:chunks] | timeline:<workload>[:exchange] (N > 1: where the step goes, CUDA-graph replay) |
+#       sweep:<workload>[:rounds[:ctas]] (N > 1: exchange rounds x push grid) | compare (the reference's own CUDA kernels beside ours, sorted and sorted=False) |
 #       env:<NAME=VALUE> (exported for the legs that follow)
 TAG=$1; shift
 OUT=gpurun_out/$TAG
@@ -58,6 +59,9 @@ PY
     timeline:*) IFS=: read -r _ wl ex <<< "$leg"
       timeout 300 $TRUN scripts/exchange_timeline.py $wl ${ex:-push} 2>$OUT/timeline_${wl}_${ex:-push}.err | grep -E "N=|rows pushed|rounds|graph|rror" | tee -a $OUT/timeline.txt
       tail -2 $OUT/timeline_${wl}_${ex:-push}.err;;
+    sweep:*) IFS=: read -r _ wl rounds ctas <<< "$leg"
+      timeout 300 $TRUN scripts/exchange_sweep.py $wl ${rounds:-1,2,3} ${ctas:-296,592} 2>$OUT/sweep_$wl.err | grep -E "N=|rror" | tee -a $OUT/sweep.txt
+      tail -2 $OUT/sweep_$wl.err;;
     shards:*) IFS=: read -r _ wl parts <<< "$leg"
       timeout 300 python scripts/shard_probe.py $wl ${parts:-8} 2>&1 | grep -E "shard|rror" | tee -a $OUT/shard_probe.txt;;
     tune:*) IFS=: read -r _ wl chunks <<< "$leg"

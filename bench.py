@@ -309,7 +309,9 @@ class Runner:
                 # phases: 0 = the library's choice (push at >= 6 GPUs: the exchange in two rounds, each followed by its edges)
                 self.bg = gdist.BucketedGather(sh, transport="push" if self.exchange == "push" else "allgather",
                                                passes=int(os.environ.get("GEOT_B200_EXCHANGE_PASSES", "0")),
-                                               phases=int(os.environ.get("GEOT_B200_EXCHANGE_PHASES", "0")))
+                                               phases=int(os.environ.get("GEOT_B200_EXCHANGE_PHASES", "0")),
+                                               phase_steps=([int(v) for v in os.environ["GEOT_B200_EXCHANGE_STEPS"].split(",")]
+                                                            if os.environ.get("GEOT_B200_EXCHANGE_STEPS") else None))
                 self.exchanged = self.bg.exchanged_rows()
         else:
             self.di, self.si, self.w, self.S, self.row0 = wk["di"], wk["si"], w, wk["S"], 0
@@ -378,12 +380,15 @@ def barrier(world):
 
 def time_runner(r, steps, warmup, sampler=None):
     """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream, max
-    over ranks.  Returns (ms per step, main-kernel ms per step)."""
+    over ranks.  The main kernel's own duration comes from a SECOND loop of K steps with the library's profiling hook
+    on (an event pair around every main-kernel launch): the timed loop itself carries no instrumentation -- an event
+    record between the main kernel and its programmatically dependent fixup launch would serialise the two and cost
+    the small shapes several microseconds per step.  Returns (ms per step, main-kernel ms per step)."""
     import torch.distributed as dist
     abi = r.abi
     for _ in range(max(warmup, 3)):
         r.step()
-    abi.profile_enable(steps * r.calls_per_step)
+    abi.profile_enable(0)
     if sampler is not None:
         sampler.start()
     barrier(r.world)
@@ -394,6 +399,10 @@ def time_runner(r, steps, warmup, sampler=None):
     ev[1].record()
     barrier(r.world)
     total_ms = ev[0].elapsed_time(ev[1])
+    abi.profile_enable(steps * r.calls_per_step)
+    for _ in range(steps):
+        r.step()
+    barrier(r.world)
     kernel_ms = abi.profile_read(steps * r.calls_per_step)
     abi.profile_enable(0)
     kmean = (sum(kernel_ms) / steps) if kernel_ms else 0.0
@@ -671,7 +680,8 @@ def run_own(args):
                 "kernel_share_of_step": round(kmean / ms_per_step, 4), "peak_source": peak_src,
                 "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                 "note": "achieved = logical bytes per launch (rank 0's shard at N > 1) / CUDA-event duration of the main kernel "
-                        "alone (events recorded by the library around it; N > 1: both bucket launches of a step, slowest rank).  "
+                        "alone (events recorded by the library around it, in a second loop of the same K steps run right after the timed loop, "
+                        "so that the timed steps carry no instrumentation; N > 1: all reduction launches of a step, slowest rank).  "
                         "For gathers the logical bytes include L2-served re-reads of src rows (SURVEY 8d), so `frac` = "
                         "frac_logical can exceed 1 and is NOT an HBM fraction: frac_dram (ncu dram bytes / kernel time) is what "
                         "the DRAM interface carried, frac_compulsory what it had to carry at least (%d bytes per launch)" % k_comp}

@@ -295,7 +295,7 @@ class BucketedGather:
     PUSH_CTAS = 2 * 148        # grid of a push that runs beside a reduction (geot_b200_push_rows_ex)
 
     def __init__(self, shard: GraphShard, group=None, transport: str = "allgather", reducer=None, allocator=None,
-                 pusher=None, barrier=None, passes: int = 0, phases: int = 0):
+                 pusher=None, barrier=None, passes: int = 0, phases: int = 0, phase_steps=None):
         assert transport in ("allgather", "push") and passes in (0, 1, 2) and phases >= 0
         assert shard.src_index is not None
         self.shard, self.group, self.transport = shard, group, transport
@@ -315,6 +315,9 @@ class BucketedGather:
             phases = 1
         phases = min(phases, max(self.world - 1, 1))
         self.phase_steps = [((self.world - 1) * (p + 1)) // phases for p in range(phases)]      # ascending, last = world-1
+        if phase_steps is not None and transport == "push" and self.world > 2:                 # explicit round boundaries
+            self.phase_steps = sorted(set(int(v) for v in phase_steps if 0 < int(v) < self.world - 1)) + [self.world - 1]
+            phases = len(self.phase_steps)
         perm, bounds = split_local_remote(shard, self.phase_steps)
         n_local = bounds[1]
         if passes == 0:

@@ -9,7 +9,9 @@ import torch.distributed as dist
 import bench
 
 name = sys.argv[1] if len(sys.argv) > 1 else "reddit_gws"
-rounds = [int(v) for v in (sys.argv[2] if len(sys.argv) > 2 else "1,2,3").split(",")]
+# rounds: counts ("1,2,3": equal rounds) or explicit last steps of the rounds joined by '+' ("1+3,2+4": rounds ending at
+# exchange steps 1, 3, N-1 and 2, 4, N-1)
+rounds = (sys.argv[2] if len(sys.argv) > 2 else "1,2,3").split(",")
 ctas = [int(v) for v in (sys.argv[3] if len(sys.argv) > 3 else "296,592").split(",")]
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -35,7 +37,12 @@ def timed(fn, n=20, warm=5):
 
 ref = None
 for k in rounds:
-    os.environ["GEOT_B200_EXCHANGE_PHASES"] = str(k)
+    os.environ.pop("GEOT_B200_EXCHANGE_STEPS", None)
+    if "+" in k or k.startswith("s"):
+        os.environ["GEOT_B200_EXCHANGE_STEPS"] = k.lstrip("s").replace("+", ",")
+        os.environ["GEOT_B200_EXCHANGE_PHASES"] = "0"
+    else:
+        os.environ["GEOT_B200_EXCHANGE_PHASES"] = k
     r = bench.Runner(wk, world, rank, dev, "push")
     for c in ctas:
         os.environ["GEOT_B200_PUSH_CTAS"] = str(c)
@@ -46,8 +53,8 @@ for k in rounds:
         same = torch.tensor([0.0 if torch.allclose(r.out, ref, rtol=1e-5, atol=0) else 1.0], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print("%s push N=%d rounds %d (asked %d) push ctas %d: %.4f ms/step, launches/step %d, equal to the first form within 1e-5: %s"
-                  % (name, world, r.phases, k, c, ms, r.calls_per_step, same.item() == 0), flush=True)
+            print("%s push N=%d rounds %d (asked %s; last steps %s) push ctas %d: %.4f ms/step, launches/step %d, equal to the first form within 1e-5: %s"
+                  % (name, world, r.phases, k, r.bg.phase_steps, c, ms, r.calls_per_step, same.item() == 0), flush=True)
     del r
     torch.cuda.empty_cache()
 dist.barrier()

@@ -20,12 +20,14 @@ for rank in range(world):
     out = torch.empty([S] + list(x.shape[1:]), dtype=wk["dtype"], device="cuda")
     f = lambda: abi.segment_reduce(x, sh.src_index, sh.dst_index, sh.weight, "sum", S=S, H=H, plan=plan, out=out, workspace=ws)
     for _ in range(3): f()
-    abi.profile_enable(10)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10): f()
     e1.record(); torch.cuda.synchronize()
+    abi.profile_enable(10)
+    for _ in range(10): f()
+    torch.cuda.synchronize()
     km = abi.profile_read(10); abi.profile_enable(0)
     deg = torch.bincount(sh.dst_index, minlength=S)
     print("%s shard %d/%d: rows %d edges %d max_degree %d has_gaps %d: step %.3f ms main kernel %.3f ms" % (

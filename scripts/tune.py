@@ -34,12 +34,14 @@ for c in chunks:
     f = lambda: abi.segment_reduce(wk["x"], wk["si"], wk["di"], w, "sum", S=S, H=H, weight_layout=layout, plan=plan, out=out, workspace=ws,
                                    src_blocks=blocks)
     for _ in range(3): f()
-    abi.profile_enable(10 * calls)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10): f()
     e1.record(); torch.cuda.synchronize()
+    abi.profile_enable(10 * calls)              # the kernel's own time from a second, instrumented loop
+    for _ in range(10): f()
+    torch.cuda.synchronize()
     km = abi.profile_read(10 * calls); abi.profile_enable(0)
     ms = e0.elapsed_time(e1) / 10
     err = float(((out.float() - ref.float()).abs() / ref.float().abs().clamp_min(1e-20)).max())

@@ -24,7 +24,7 @@ SYMBOLS = [
     "geot_b200_gather_scatter", "geot_b200_gather_weight_scatter", "geot_b200_mh_spmm",
     "geot_b200_sddmm_coo", "geot_b200_csr_to_coo", "geot_b200_permute_edges",
     "geot_b200_segment_reduce_host", "geot_b200_host_arena_release", "geot_b200_profile_enable", "geot_b200_profile_read",
-    "geot_b200_push_rows", "geot_b200_push_rows_ex",
+    "geot_b200_push_rows", "geot_b200_push_rows_ex", "geot_b200_set_unsorted_mode",
     "geot_b200_host_last_transfer", "geot_b200_host_row_pointers", "geot_b200_segment_reduce_ex",
     "geot_b200_host_graph_create", "geot_b200_host_graph_reduce", "geot_b200_host_graph_last_transfer",
     "geot_b200_host_graph_destroy", "geot_b200_src_blocks_suggest", "geot_b200_src_blocks_bytes",
@@ -106,6 +106,7 @@ def lib() -> ctypes.CDLL:
         L.geot_b200_push_rows_ex.argtypes = [vp, vp, vp, vp, vp, i64, i64, ci, ci, vp]
         L.geot_b200_host_last_transfer.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
         L.geot_b200_host_row_pointers.argtypes = [vp, i64, i64, i64, vp, ci]
+        L.geot_b200_set_unsorted_mode.argtypes = [ci]
         _lib = L
     return _lib
 

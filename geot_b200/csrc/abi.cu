@@ -219,6 +219,64 @@ __global__ void gather_index_kernel(const int64_t *__restrict__ perm, const int6
   if (i < n) out[i] = in[perm[i]];
 }
 
+// ---- index_scatter(sorted = False), sum, fp32: 128-bit vector atomics ------------------------------------------------
+// The reference's unsorted kernel (scatter_reduce_kernel, csrc/cuda/index_scatter_kernel.cuh:204-263) issues one scalar
+// atomicAdd per element after a torch::zeros.  Here every thread streams 16 bytes of src (read once: evict-first) and
+// adds them with ONE red.global.add.v4.f32 (REDG.E.ADD.F32x4, sm_90+): a quarter of the atomic operations, the dst
+// rows stay in L2.  Like the reference's, the summation order is the hardware's: not bit-reproducible run to run
+// (geot_b200_set_unsorted_mode(1) selects the deterministic sort-based path instead; it is what every other dtype and
+// reduce op uses).  Measured beside the reference kernel by scripts/compare_reference_cuda.py unsorted.
+__device__ __forceinline__ void red_add(float *q, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add(float *q, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_once(const float4 *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ld_once(const float *p, uint64_t pol) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+constexpr int kScatterUnroll = 4;
+// V = float4 (rows of whole 16-byte pieces) or float; `pieces` = pieces per row, shift = log2(pieces) or -1
+template <typename V>
+__global__ void __launch_bounds__(256)
+scatter_add_kernel(const V *__restrict__ src, const int64_t *__restrict__ src_index, const int64_t *__restrict__ index,
+                   float *__restrict__ dst, int64_t E, int pieces, int shift, int64_t S) {
+  constexpr int PW = (int)(sizeof(V) / sizeof(float));
+  const int64_t total = E * pieces;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint64_t pol = geot::policy_evict_first();
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * kScatterUnroll) {
+    V v[kScatterUnroll];
+    float *q[kScatterUnroll];
+#pragma unroll
+    for (int u = 0; u < kScatterUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      q[u] = nullptr;
+      if (i < total) {
+        const int64_t e = shift >= 0 ? (i >> shift) : (i / pieces);
+        const int64_t k = i - e * pieces;
+        const int64_t row = index[e];
+        const int64_t srow = src_index ? src_index[e] : e;
+        v[u] = ld_once(src + srow * pieces + k, pol);
+        if (row >= 0 && row < S) q[u] = dst + (row * pieces + k) * PW;    // (an index outside [0, S) is dropped, not written)
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kScatterUnroll; ++u)
+      if (q[u] != nullptr) red_add(q[u], v[u]);
+  }
+}
+
+int g_unsorted_mode = 0;      // 0: vector atomics where they apply (fp32 sum); 1: always the deterministic sort path
+
 // CSR row pointer -> COO row index: one thread per edge, binary search of the edge position in rowptr
 // (upper bound - 1).  Rows are found independently, so the kernel is a single coalesced write pass.
 template <typename P>
@@ -436,6 +494,26 @@ int segment_reduce_impl(const void *src, const int64_t *src_index, const int64_t
   // reference uses an all-atomic kernel here (index_scatter_kernel.cuh:204-263).
   const int64_t *d_dst = dst_index, *d_src = src_index;
   if (!sorted && weight) return GEOT_ERR_UNSUPPORTED;  // weights follow the edge order: sorted input only
+  if (!sorted && reduce == GEOT_SUM && dtype == GEOT_F32 && !opts && g_unsorted_mode == 0 && env_int("GEOT_B200_UNSORTED_SORT", 0) == 0) {
+    // fp32 sum: clear dst, then one pass of vector atomics (see scatter_add_kernel)
+    CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)S * (size_t)W * sizeof(float), stream));
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const int64_t pieces = vec ? W / 4 : W;
+    if (pieces > 0x7fffffffLL) return GEOT_ERR_UNSUPPORTED;
+    int shift = -1;
+    if ((pieces & (pieces - 1)) == 0) { shift = 0; while ((1LL << shift) < pieces) ++shift; }
+    const int64_t total = E * pieces;
+    const int64_t need = (total + 256LL * kScatterUnroll - 1) / (256LL * kScatterUnroll);
+    const unsigned blocks = (unsigned)std::min<int64_t>(need, 148LL * 8);
+    if (vec)
+      scatter_add_kernel<float4><<<blocks, 256, 0, stream>>>(static_cast<const float4 *>(src), src_index, dst_index,
+                                                             static_cast<float *>(dst), E, (int)pieces, shift, S);
+    else
+      scatter_add_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float *>(src), src_index, dst_index,
+                                                            static_cast<float *>(dst), E, (int)pieces, shift, S);
+    CUDA_TRY(cudaGetLastError());
+    return GEOT_OK;
+  }
   if (!sorted) {
     const size_t ebytes = align256((size_t)E * 8);
     size_t cub_bytes = 0;
@@ -614,6 +692,12 @@ int geot_b200_mh_spmm(const void *src, const int64_t *src_index, const int64_t *
   if (weight_layout != GEOT_W_EDGE_HEAD && weight_layout != GEOT_W_HEAD_EDGE) return GEOT_ERR_INVALID_ARG;
   return geot_b200_segment_reduce(src, src_index, dst_index, weight, dst, E, S, H, F, dtype, reduce, weight_layout, 1,
                                   plan, workspace, workspace_bytes, stream);
+}
+
+int geot_b200_set_unsorted_mode(int mode) {
+  if (mode != 0 && mode != 1) return GEOT_ERR_INVALID_ARG;
+  g_unsorted_mode = mode;
+  return GEOT_OK;
 }
 
 int geot_b200_profile_enable(int n) {

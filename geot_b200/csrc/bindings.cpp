@@ -239,13 +239,17 @@ at::Tensor run(const char *what, const at::Tensor &src_in, const c10::optional<a
   const geot_plan_t *plan_ptr = nullptr;
   at::Tensor plan_buf;
   int64_t S;
-  if (sorted) {
-    plan = get_plan(dst_index, &plan_buf);
-    TORCH_CHECK(plan.is_sorted, "geot::", what, ": index is not sorted (pass sorted=False to index_scatter)");
+  plan = get_plan(dst_index, &plan_buf);        // cached per index tensor: no pass over the index, no sync on later calls
+  if (sorted) TORCH_CHECK(plan.is_sorted, "geot::", what, ": index is not sorted (pass sorted=False to index_scatter)");
+  if (plan.is_sorted) {
+    // sorted=False with an index that IS sorted -- what the reference's own test and benchmark pass
+    // (test/test_index_scatter.py:9-14, benchmark/bench_index_scatter.py:32) -- takes the sorted kernels
+    sorted = true;
     plan_ptr = &plan;
     S = plan.S;
   } else {
-    S = dst_index.max().item<int64_t>() + 1;
+    S = plan.max_row + 1;                       // (the plan's row pointers mean nothing for an unsorted index: not passed on)
+    check_status(geot_b200_set_unsorted_mode(at::globalContext().deterministicAlgorithms() ? 1 : 0), what);
   }
   // min_rows > S: the caller wants trailing rows that no edge reaches (csr_gws); they are zero-filled here and the
   // kernels see the [S, W] prefix

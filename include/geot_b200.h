@@ -19,7 +19,8 @@
  * dst has S rows and is fully overwritten; rows that receive no edge are 0.  op in
  * {sum, mean, max, min, prod}; mean = sum / count; max/min propagate NaN (torch amax/amin).
  * fp32 and fp64 accumulate in their own type, bf16/fp16 accumulate in fp32 and round once.
- * The reduction is deterministic (fixed tree, no atomics) for sorted dst_index.
+ * The reduction is deterministic (fixed tree, no atomics) for sorted dst_index, and for unsorted input unless the
+ * fp32-sum vector-atomic path is in use (geot_b200_set_unsorted_mode).
  */
 #ifndef GEOT_B200_H_
 #define GEOT_B200_H_
@@ -184,8 +185,11 @@ GEOT_API int geot_b200_src_blocks_build(const int64_t *src_index, const int64_t 
 GEOT_API size_t geot_b200_src_blocks_workspace_bytes(const geot_src_blocks_t *blocks, int64_t W, int dtype);
 
 /* Replaces index_scatter_cuda (header_cuda.h:4-6; csrc/cuda/index_scatter_cuda.cu:86-105), dim = 0:
- * src viewed as [E, F] (wrapper/index_scatter_base.h:15-17).  sorted == 0 takes the atomic kernel
- * (index_scatter_cuda.cu:75-84). */
+ * src viewed as [E, F] (wrapper/index_scatter_base.h:15-17).  sorted == 0 replaces the reference's all-atomic
+ * scatter_reduce_kernel (index_scatter_cuda.cu:75-84, index_scatter_kernel.cuh:204-263): fp32 sum clears dst and adds
+ * 16-byte pieces with vector atomics (red.global.add.v4.f32; summation order = the hardware's, as in the reference);
+ * every other dtype / reduce op -- and fp32 sum after geot_b200_set_unsorted_mode(1) -- sorts the edge ids by row
+ * (stable) and runs the deterministic sorted kernels. */
 GEOT_API int geot_b200_index_scatter(const void *src, const int64_t *index, void *dst, int64_t E, int64_t S,
                             int64_t F, int dtype, int reduce, int sorted, const geot_plan_t *plan,
                             void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -298,6 +302,11 @@ GEOT_API int geot_b200_host_last_transfer(unsigned long long *h2d_bytes, unsigne
  * segment-pointer pass of the reference's CPU kernel (csrc/cpu/index_scatter_cpu.cpp:36-75).  threads <= 0: all. */
 GEOT_API int geot_b200_host_row_pointers(const int64_t *index, int64_t n, int64_t row0, int64_t rows, int64_t *rowptr,
                                 int threads);
+
+/* sorted == 0 policy, process-wide: 0 (default) = vector atomics where they apply (fp32 sum: fastest, not
+ * bit-reproducible run to run); 1 = always the deterministic sort-based path.  The torch bindings select 1 while
+ * torch.use_deterministic_algorithms(True) is in force. */
+GEOT_API int geot_b200_set_unsorted_mode(int mode);
 
 /* ---- instrumentation -------------------------------------------------------------------------- */
 

@@ -107,7 +107,8 @@ def main():
 
 
 def unsorted():
-    """index_scatter(sorted=False): ours = stable radix sort of the edge ids + the deterministic sorted kernels; the
+    """index_scatter(sorted=False): ours = vector atomics for fp32 sum (the deterministic alternative -- stable radix sort
+    of the edge ids + the sorted kernels -- timed beside it); the
     reference = its all-atomic scatter_reduce_kernel (csrc/cuda/index_scatter_kernel.cuh:204-263), which is the variant
     its own test and benchmark call (test/test_index_scatter.py:14, benchmark/bench_index_scatter.py:32)."""
     have_ref = oracle.load_ref_extension()
@@ -120,6 +121,13 @@ def unsorted():
         rec = {"workload": "index_scatter sorted=False, random index", "E": E, "S": S, "F": F, "dtype": "f32"}
         b, m = timed(ours)
         rec["ours_dropin_call_ms"] = {"best": round(b, 4), "median": round(m, 4)}
+        rec["ours_path"] = "vector atomics (red.global.add.v4.f32) after a memset; S from the cached plan"
+        torch.use_deterministic_algorithms(True)          # the sort-based deterministic path
+        try:
+            bd, md = timed(ours)
+        finally:
+            torch.use_deterministic_algorithms(False)
+        rec["ours_deterministic_sort_path_ms"] = {"best": round(bd, 4), "median": round(md, 4)}
         si_sorted, perm = torch.sort(idx, stable=True)
         xs = x[perm].contiguous()
         b2, m2 = timed(lambda: geot_b200.index_scatter(0, xs, si_sorted, "sum", True))

@@ -296,6 +296,38 @@ def test_unsorted_detection_and_unsorted_path():
         assert_close(got, exp, torch.float32, red, "unsorted " + red)
 
 
+@pytest.mark.parametrize("F", [1, 3, 32, 64, 100, 130])
+def test_unsorted_sum_vector_atomics_and_deterministic_mode(F):
+    """index_scatter(sorted=False), fp32 sum: the vector-atomic path (red.global.add.v4.f32; scalar for rows that are
+    not whole 16-byte pieces) against the oracle, with rows that receive no edge; under
+    torch.use_deterministic_algorithms the sort-based path runs instead and is bit-reproducible; an index that is in
+    fact sorted takes the sorted kernels whatever the flag says (the reference's own test passes sorted=False on a
+    sorted index, test/test_index_scatter.py:9-14)."""
+    g = torch.Generator().manual_seed(F)
+    E, N = 30000, 257
+    idx = torch.randint(0, N, (E,), generator=g)
+    idx[idx == 7] = 8                                   # row 7 receives nothing
+    idx[-1] = 11                                        # the last entry is NOT the largest: S comes from the plan's max
+    src = torch.rand(E, F, generator=g)
+    exp = oracle.index_scatter(0, idx, src, "sum", acc64=True)
+    got = geot_b200.index_scatter(0, src.to(DEV), idx.to(DEV), "sum", sorted=False)
+    assert got.shape[0] == int(idx.max()) + 1 and float(got[7].abs().sum()) == 0.0
+    assert_close(got, exp, torch.float32, "sum", "unsorted atomics F=%d" % F)
+    torch.use_deterministic_algorithms(True)
+    try:
+        d1 = geot_b200.index_scatter(0, src.to(DEV), idx.to(DEV), "sum", sorted=False)
+        d2 = geot_b200.index_scatter(0, src.to(DEV), idx.to(DEV), "sum", sorted=False)
+    finally:
+        torch.use_deterministic_algorithms(False)
+    assert torch.equal(d1, d2)
+    assert_close(d1, exp, torch.float32, "sum", "unsorted deterministic F=%d" % F)
+    sidx, perm = torch.sort(idx, stable=True)
+    ssrc = src[perm].contiguous().to(DEV)
+    a = geot_b200.index_scatter(0, ssrc, sidx.to(DEV), "sum", sorted=False)
+    b = geot_b200.index_scatter(0, ssrc, sidx.to(DEV), "sum", sorted=True)
+    assert torch.equal(a, b)
+
+
 # ------------------------------------------------------------------------------------------------
 # operator-level behaviour (drop-in surface)
 # ------------------------------------------------------------------------------------------------

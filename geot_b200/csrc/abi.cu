@@ -546,6 +546,10 @@ int segment_reduce_impl(const void *src, const int64_t *src_index, const int64_t
   const Config cfg = choose_config(E, W, F, dtype, aligned, d_src != nullptr);
   Workspace w = carve(ws, cfg.n_tiles, W, dtype);
   if (w.bytes > ws_left) return GEOT_ERR_WORKSPACE;
+  // The lean ring carries dst row ids and src row ids (index_scatter: edge ids) as 32-bit values.  A ring row is >= 128
+  // bytes, so neither can reach 2^32 on a 180 GB device -- but the launcher does not rely on that: beyond 32 bits the
+  // first-generation ring (64-bit offsets) is selected.
+  const bool ids_fit_32 = S <= 0xffffffffLL && (d_src != nullptr || E <= 0xffffffffLL);
 
   // Rows that receive no edge must read 0.  The kernels store every non-empty row exactly once; the rows in between
   // are zero-filled INSIDE the main kernel by the group that sees the jump in the (sorted) index, so there is no
@@ -577,6 +581,7 @@ int segment_reduce_impl(const void *src, const int64_t *src_index, const int64_t
   if (weight_layout == GEOT_W_EDGE_HEAD) { p.ws_e = H; p.ws_h = 1; }
   if (weight_layout == GEOT_W_HEAD_EDGE) { p.ws_e = 1; p.ws_h = E; }
   geot::Shape shape = cfg.shape;
+  if (!ids_fit_32 && (shape.pf & geot::kLeanFlag)) shape.pf = (shape.vpl == 1) ? 3 : 2;
   shape.wm = !weight ? geot::WM_NONE : (H == 1 ? geot::WM_EDGE : geot::WM_GENERIC);
   p.mean = (reduce == GEOT_MEAN);
   p.accumulate = accumulate ? 1 : 0;

@@ -151,21 +151,3 @@ def forward_sharded(model: _Stack, x_local: torch.Tensor, shard, group=None, gat
             out = conv.lin_l(agg) + conv.lin_r(x)
         x = torch.relu(out) if i + 1 < len(model.convs) else out
     return x
-
-
-def reference_forward(model: _Stack, x: torch.Tensor, src_index, dst_index, norm_weight=None) -> torch.Tensor:
-    """Plain-torch restatement (``index_select -> mul -> index_add_``) of the same stack: the formula the
-    reference's compile tests compare against (``test/compile/test_gcn.py``); used by the tests only."""
-    n = x.shape[0]
-    for i, conv in enumerate(model.convs):
-        if isinstance(conv, GCNConv):
-            h = conv.lin(x)
-            out = torch.zeros(n, h.shape[1], dtype=h.dtype, device=h.device).index_add_(
-                0, dst_index, norm_weight.unsqueeze(-1) * h.index_select(0, src_index))
-            if conv.bias is not None:
-                out = out + conv.bias
-        else:
-            agg = torch.zeros(n, x.shape[1], dtype=x.dtype, device=x.device).index_add_(0, dst_index, x.index_select(0, src_index))
-            out = conv.lin_l(agg) + conv.lin_r(x)
-        x = torch.relu(out) if i + 1 < len(model.convs) else out
-    return x

@@ -261,14 +261,15 @@ def _worker(rank, world, port, q, hub=False):
     # 3-layer GCN / GraphSAGE forward on the shard (BASELINE configs[4] at N > 1): every layer through the bucketed
     # exchange (both transports; hidden width != input width: per-shape buffers), against the plain-torch restatement
     from geot_b200 import gnn
+    from tests.helpers import gnn_restatement as restate
     torch.manual_seed(7)                                  # same random weights on every rank
     gcn, sage = gnn.GCN(F, 16, 3), gnn.GraphSAGE(F, 16, 3)
     norm = gnn.gcn_norm(src_index, dst, N, weight)
     sh_gcn = gdist.shard_graph(src_index, dst, norm, rank, world, row_bounds=rb, edge_bounds=eb)
     sh_sage = gdist.shard_graph(src_index, dst, None, rank, world, row_bounds=rb, edge_bounds=eb)
     with torch.no_grad():
-        exp_gcn = gnn.reference_forward(gcn, x, src_index, dst, norm)[rb[rank]:rb[rank + 1]]
-        exp_sage = gnn.reference_forward(sage, x, src_index, dst)[rb[rank]:rb[rank + 1]]
+        exp_gcn = restate.forward(gcn, x, src_index, dst, norm)[rb[rank]:rb[rank + 1]]
+        exp_sage = restate.forward(sage, x, src_index, dst)[rb[rank]:rb[rank + 1]]
         for kw in (dict(transport="allgather", reducer=reducer), kw_push):
             got = gnn.forward_sharded(gcn, x_local, sh_gcn, gather=gdist.BucketedGather(sh_gcn, **kw))
             assert torch.allclose(got, exp_gcn, rtol=1e-4, atol=1e-5), ("gcn", kw["transport"])

@@ -162,3 +162,32 @@ def test_config1_index_scatter_full_oracle():
         assert torch.equal(out.cpu(), oracle.index_scatter(0, index.cpu(), src.cpu(), red))
     plan = geot_b200.format_preprocess(index)
     assert torch.equal(plan.rowptr.cpu(), oracle.rowptr(index.cpu(), S))
+
+
+def test_proteins_shape_gcn_and_graphsage_forward_full_size():
+    """BASELINE configs[4] at its FULL shape (132 534 nodes, 39.6 M edges, 256-256-256-256, fp32): the 3-layer GCN and
+    GraphSAGE forward through the operators against the plain-torch restatement of the same stacks with the aggregation
+    accumulated in fp64 (tests/helpers/gnn_restatement.py; the reference's models: models/gcn.py:35-60,
+    models/graphsage.py:26-64).  Tolerance: 2e-4 of the largest output per layer stack (fp32 GEMMs, TF32 off, between
+    the aggregations)."""
+    import workloads as wl
+    from geot_b200 import gnn
+    from tests.helpers import gnn_restatement as restate
+    graph = wl.power_law_graph("proteins", DEV)
+    N, si, di = graph.num_nodes, graph.src_index, graph.dst_index
+    assert N == 132_534 and si.numel() > 39_000_000
+    torch.manual_seed(0)
+    x = torch.rand(N, 256, device=DEV)
+    norm = gnn.gcn_norm(si, di, N)
+    gcn = gnn.GCN(256, 256, 3).to(DEV)
+    sage = gnn.GraphSAGE(256, 256, 3).to(DEV)
+    with torch.no_grad():
+        for p in sage.parameters():                      # sum aggregation over ~300 neighbours per layer: keep activations O(1)
+            p.mul_(0.05)
+        for model, args in ((gcn, (norm,)), (sage, ())):
+            out = model(x, si, di, *args)
+            ref = restate.forward(model, x, si, di, *args, acc_dtype=torch.float64)
+            assert out.shape == (N, 256) and bool(torch.isfinite(out).all())
+            scale = float(ref.abs().max())
+            err = float((out - ref).abs().max())
+            assert err <= 2e-4 * scale, (type(model).__name__, err, scale)

@@ -8,6 +8,7 @@ import pytest
 import torch
 
 import oracle
+from tests.helpers import gnn_restatement as restate
 
 pytestmark = pytest.mark.gpu
 
@@ -156,11 +157,11 @@ def test_gcn_and_graphsage_forward_match_torch_restatement():
         for p in list(gcn.parameters()) + list(sage.parameters()):     # keep activations O(1) through sum aggregation
             p.mul_(0.05)
         out = gcn(x, si, di, norm)
-        ref = gnn.reference_forward(gcn, x.double(), si, di, norm.double()) if False else gnn.reference_forward(gcn, x, si, di, norm)
+        ref = restate.forward(gcn, x, si, di, norm, acc_dtype=torch.float64)
         assert out.shape == (N, 256)
         assert torch.allclose(out, ref, rtol=1e-3, atol=1e-4)
         out = sage(x, si, di)
-        ref = gnn.reference_forward(sage, x, si, di)
+        ref = restate.forward(sage, x, si, di, acc_dtype=torch.float64)
         assert torch.allclose(out, ref, rtol=1e-3, atol=1e-3 * float(ref.abs().max()))
     # the aggregation alone (no GEMM in between) holds the op-level tolerance against the oracle
     h = torch.rand(N, 256, device=DEV)

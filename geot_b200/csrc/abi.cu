@@ -82,9 +82,10 @@ Config choose_config(int64_t E, int64_t W, int64_t F, int dtype, bool vector_ok,
   int chunk = env_int("GEOT_B200_CHUNK", 0);
   if (chunk <= 0) {
     chunk = 256;
-    // at least 4 tiles per SM (measured on the two small BASELINE shapes, profiles/r02a_chunk_sweep_small.txt: arxiv
-    // mh_spmm 0.198 ms at chunk 32 -> 0.171 at 128; config #1 index_scatter 0.070 at 256 -> 0.064 at 64)
-    while (chunk > 8 && (E + (int64_t)ng * chunk - 1) / ((int64_t)ng * chunk) < 4 * 148) chunk >>= 1;
+    // at least 3.5 tiles per SM (measured on the two small BASELINE shapes, profiles/r02a_chunk_sweep_small.txt and
+    // r02s_tune.txt: config #1 index_scatter 0.064 ms at chunk 128 = 489 tiles -> 0.057 at 64 = 977; arxiv mh_spmm 0.128 at
+    // 128 = 1139 tiles -> 0.116 at 256 = 570)
+    while (chunk > 8 && (E + (int64_t)ng * chunk - 1) / ((int64_t)ng * chunk) < 518) chunk >>= 1;
   }
   // (Sizing the grid in whole waves of resident CTAs -- shrinking the chunk until the tiles fill an integer number of
   // waves -- was measured on the shapes that are only a few waves deep and changed nothing: config #1 0.065 / 0.066 ms,

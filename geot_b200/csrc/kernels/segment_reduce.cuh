@@ -570,8 +570,31 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
                 for (int j = 0; j < VPL; ++j) we[j] = wv[j].v[u];
                 add_edge(v[u], we);
               }
+            } else if constexpr (!kExt && VPL == 1 && LPR >= 16) {
+              // a dst row starts inside these U edges: the same adds, straight from the registers, with the open run
+              // closed in front of every edge that starts a row.  Only the close is a branch (a warp of two or four
+              // groups diverges for the few instructions of the store, not for the edges), and nothing is read twice --
+              // on short-row graphs (products: 25 edges per row, arxiv: 7) up to half of the sub-batches come here.
+              // (The instantiation with the segment_reduce_ex options, rows wider than 512 bytes and 128-byte rows keep
+              // the rolled loop below: unrolled, their larger close paths spill.)
+#pragma unroll
+              for (int u = 0; u < U; ++u) {
+                if ((sub >> u) & 1u) {
+                  const int k = pos + t * U + u;          // chunk-relative position of this edge
+                  const int kb = k - batch_pos;           // position inside the batch
+                  const uint32_t row = __shfl_sync(gmask, d_cur, kb > 0 ? kb - 1 : 0, LPR);
+                  const int64_t prev = (int64_t)(kb > 0 ? row : batch_left);
+                  cnt = k - run_start;
+                  close_run(prev, prev + 1);
+                  run_start = k;
+                }
+                float we[VPL];
+#pragma unroll
+                for (int j = 0; j < VPL; ++j) we[j] = wv[j].v[u];
+                add_edge(v[u], we);
+              }
             } else {
-              // a dst row starts inside these U edges: one edge at a time, operands re-read from shared memory
+              // ... one edge at a time, operands re-read from shared memory
 #pragma unroll 1
               for (int u = 0; u < U; ++u) {
                 const int k = pos + t * U + u;            // chunk-relative position of this edge

@@ -570,13 +570,15 @@ segment_reduce_kernel(const __grid_constant__ Params p) {
                 for (int j = 0; j < VPL; ++j) we[j] = wv[j].v[u];
                 add_edge(v[u], we);
               }
-            } else if constexpr (!kExt && VPL == 1 && LPR >= 16) {
+            } else if constexpr (!kExt && !HEADW && VPL == 1 && LPR >= 16) {
               // a dst row starts inside these U edges: the same adds, straight from the registers, with the open run
               // closed in front of every edge that starts a row.  Only the close is a branch (a warp of two or four
               // groups diverges for the few instructions of the store, not for the edges), and nothing is read twice --
               // on short-row graphs (products: 25 edges per row, arxiv: 7) up to half of the sub-batches come here.
+              // products gs64 1.52 -> 1.46 ms, its 8 shards 0.221-0.257 -> 0.212-0.245 (profiles/r02s_tune.txt, r02t_tune.txt).
               // (The instantiation with the segment_reduce_ex options, rows wider than 512 bytes and 128-byte rows keep
-              // the rolled loop below: unrolled, their larger close paths spill.)
+              // the rolled loop below: unrolled, their larger close paths spill; with per-head weights the unrolled form
+              // needs 128 registers and ran arxiv mh_spmm 30 % SLOWER, r02t_tune.txt.)
 #pragma unroll
               for (int u = 0; u < U; ++u) {
                 if ((sub >> u) & 1u) {

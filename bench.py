@@ -58,6 +58,9 @@ WORKLOADS = {
     "reddit_index_scatter": ("reddit", "index_scatter", 128, 1, torch.float32),
     "products_gs64": ("products", "gather_scatter", 64, 1, torch.float32),
     "products_gs256": ("products", "gather_scatter", 256, 1, torch.float32),
+    # the products shape with a quarter of the dst rows isolated: shows what zero-filling rows without edges costs (it
+    # happens inside the main kernel; the reference clears all of dst first, csrc/gather_scatter.cpp:27-30)
+    "products_gs64_gaps": ("products+isolated", "gather_scatter", 64, 1, torch.float32),
     "arxiv_mh_spmm": ("arxiv", "mh_spmm", 32, 8, torch.bfloat16),
     "proteins_gws256": ("proteins", "gather_weight_scatter", 256, 1, torch.float32),
     "config1_index_scatter": ("config1", "index_scatter", 64, 1, torch.float32),
@@ -136,6 +139,8 @@ def build_workload(name, device, scale=1.0):
         E, S = 1_000_000, 50_000
         dst = wl.random_segments(E, S, device)
         g = wl.Graph("config1", S, None, dst, 0, 0.0)
+    elif gname.endswith("+isolated"):
+        g = wl.power_law_graph(gname.split("+")[0], device, scale, isolated=0.25)
     else:
         g = wl.power_law_graph(gname, device, scale)
     E, N = g.num_edges, g.num_nodes
@@ -744,12 +749,17 @@ def run_own(args):
                             "kernel-scaling number (src pre-replicated, SURVEY 8e)"}
         else:
             for name, cpu in (("reddit_index_scatter", False), ("config1_index_scatter", True), ("products_gs64", False),
-                              ("products_gs256", False), ("arxiv_mh_spmm", False)):
+                              ("products_gs64_gaps", False), ("products_gs256", False), ("arxiv_mh_spmm", False)):
                 try:
                     secondary[name] = run_secondary(name, 1, 0, dev, ["none"], sec_steps, args.warmup, peak, with_cpu=cpu)["none"]
                 except Exception as ex:       # a secondary line must not cost the headline
                     secondary[name] = {"error": repr(ex)}
                     torch.cuda.empty_cache()
+            if "error" not in secondary.get("products_gs64_gaps", {"error": 1}):
+                secondary["products_gs64_gaps"]["note"] = (
+                    "products shape with 25 % of the dst rows isolated: the rows without edges are zero-filled inside the main "
+                    "kernel by the group that sees the jump in the sorted index (no memset of dst; the parity check covers the "
+                    "empty rows); compare with products_gs64")
 
     if rank != 0:
         if world > 1:

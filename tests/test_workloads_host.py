@@ -48,3 +48,16 @@ def test_power_law_graph_shape_and_order():
     assert g.max_degree == int(deg.max()) and g.degree_cv > 0.5                            # heavy tail
     g2 = wl.power_law_graph("reddit", "cpu", scale=1 / 256)
     assert torch.equal(g.src_index, g2.src_index) and torch.equal(g.dst_index, g2.dst_index)
+
+
+def test_power_law_graph_with_isolated_rows():
+    """`isolated`: that fraction of the dst rows receives no edge (the gappy bench workload); E, N, the order and the
+    last row are kept, and the default graphs are untouched by the option."""
+    g = wl.power_law_graph("products", "cpu", scale=1 / 128, isolated=0.25)
+    n0, e0, _ = wl.SHAPES["products"]
+    assert g.num_nodes == round(n0 / 128) and g.num_edges == round(e0 / 128)
+    deg = torch.bincount(g.dst_index, minlength=g.num_nodes)
+    frac = float((deg == 0).float().mean())
+    assert 0.2 < frac < 0.3 and int(g.dst_index[-1]) == g.num_nodes - 1
+    assert bool((g.dst_index[1:] >= g.dst_index[:-1]).all())
+    assert int(torch.bincount(wl.power_law_graph("products", "cpu", scale=1 / 128).dst_index).min()) >= 1

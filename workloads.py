@@ -33,9 +33,11 @@ class Graph:
         return self.dst_index.numel()
 
 
-def power_law_graph(name: str, device="cuda", scale: float = 1.0, seed: int = 0) -> Graph:
+def power_law_graph(name: str, device="cuda", scale: float = 1.0, seed: int = 0, isolated: float = 0.0) -> Graph:
     """In-degree of node i proportional to (pi(i)+1)^-a (pi a seeded permutation), sources drawn from
-    the same heavy-tailed distribution; `scale` shrinks nodes and edges together (tests)."""
+    the same heavy-tailed distribution; `scale` shrinks nodes and edges together (tests).  `isolated` > 0: that
+    fraction of the nodes (seeded choice, never the last node) receives NO edge -- dst rows the op must zero-fill;
+    their edges go to the largest row, so E stays the shape's."""
     n0, e0, a = SHAPES[name]
     N = max(2, int(round(n0 * scale)))
     E = max(N, int(round(e0 * scale)))
@@ -43,11 +45,16 @@ def power_law_graph(name: str, device="cuda", scale: float = 1.0, seed: int = 0)
     perm = torch.randperm(N, generator=g, device=device)
     w = (perm.double() + 1.0).pow(-a)
     p = w / w.sum()
-    deg = torch.floor(p * E).long().clamp_min(1)        # every node keeps >= 1 in-edge: no empty rows
+    deg = torch.floor(p * E).long().clamp_min(1)        # every node keeps >= 1 in-edge: no empty rows ...
+    if isolated > 0:                                     # ... unless asked for
+        gone = torch.rand(N, generator=g, device=device) < isolated
+        gone[-1] = False                                 # the output keeps its N rows (S = dst[-1] + 1)
+        gone[torch.argmax(deg)] = False
+        deg[gone] = 0
     diff = E - int(deg.sum())
     top = torch.argmax(deg)
     deg[top] += diff                                     # remainder to the largest
-    assert int(deg.sum()) == E and int(deg.min()) >= 1
+    assert int(deg.sum()) == E and (isolated > 0 or int(deg.min()) >= 1)
     dst = torch.repeat_interleave(torch.arange(N, device=device), deg)
     cdf = torch.cumsum(p, 0)
     u = torch.rand(E, generator=g, device=device, dtype=torch.float64)

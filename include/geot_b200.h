@@ -119,7 +119,8 @@ GEOT_API size_t geot_b200_workspace_bytes(int64_t E, int64_t W, int dtype, int s
  *   weight     per weight_layout, dtype; NULL iff GEOT_W_NONE
  *   dst        [S, H*F]       device, dtype; fully overwritten
  *   plan       optional (NULL allowed): lets the call skip zero-filling when the graph has no
- *              empty rows; results are identical with and without it. */
+ *              empty rows, and zero exactly the empty ones up front when it has (without a plan the
+ *              main kernel fills the gaps it sees); results are identical with and without it. */
 GEOT_API int geot_b200_segment_reduce(const void *src, const int64_t *src_index, const int64_t *dst_index,
                              const void *weight, void *dst, int64_t E, int64_t S, int64_t H,
                              int64_t F, int dtype, int reduce, int weight_layout, int sorted,

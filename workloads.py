@@ -37,7 +37,7 @@ def power_law_graph(name: str, device="cuda", scale: float = 1.0, seed: int = 0,
     """In-degree of node i proportional to (pi(i)+1)^-a (pi a seeded permutation), sources drawn from
     the same heavy-tailed distribution; `scale` shrinks nodes and edges together (tests).  `isolated` > 0: that
     fraction of the nodes (seeded choice, never the last node) receives NO edge -- dst rows the op must zero-fill;
-    their edges go to the largest row, so E stays the shape's."""
+    the other nodes share the shape's E by the same law."""
     n0, e0, a = SHAPES[name]
     N = max(2, int(round(n0 * scale)))
     E = max(N, int(round(e0 * scale)))
@@ -45,12 +45,14 @@ def power_law_graph(name: str, device="cuda", scale: float = 1.0, seed: int = 0,
     perm = torch.randperm(N, generator=g, device=device)
     w = (perm.double() + 1.0).pow(-a)
     p = w / w.sum()
-    deg = torch.floor(p * E).long().clamp_min(1)        # every node keeps >= 1 in-edge: no empty rows ...
-    if isolated > 0:                                     # ... unless asked for
+    if isolated > 0:                                     # in-degrees over the nodes that keep edges, same law
         gone = torch.rand(N, generator=g, device=device) < isolated
         gone[-1] = False                                 # the output keeps its N rows (S = dst[-1] + 1)
-        gone[torch.argmax(deg)] = False
+        wd = torch.where(gone, torch.zeros_like(w), w)
+        deg = torch.floor(wd / wd.sum() * E).long().clamp_min(1)
         deg[gone] = 0
+    else:
+        deg = torch.floor(p * E).long().clamp_min(1)    # every node keeps >= 1 in-edge: no empty rows
     diff = E - int(deg.sum())
     top = torch.argmax(deg)
     deg[top] += diff                                     # remainder to the largest

@@ -224,8 +224,8 @@ __global__ void gather_index_kernel(const int64_t *__restrict__ perm, const int6
 // at or beyond the plan's S): a warp checks 32 rows, then zero-fills the empty ones cooperatively -- the writes are the
 // empty rows only, not a memset of the whole dst, and the main kernel runs its plain instantiation.  (Zero-filling inside
 // the main kernel -- the group that sees the jump in the sorted index fills the gap -- is what a call WITHOUT a plan does;
-// on the products shape with a quarter of the rows isolated it cost 0.45 ms of a 1.93 ms step against 0.03 ms here,
-// profiles/r02w_bench.json -> r02x_bench.json.)
+// on the products shape with a quarter of the rows isolated it costs 0.18 ms of the step against 0.04 ms here,
+// profiles/r02y_tune_gaps.txt.)
 __global__ void __launch_bounds__(256)
 zero_empty_rows_kernel(const int64_t *__restrict__ rowptr, int64_t plan_rows, int64_t S, int64_t row_bytes, char *dst, int vec16) {
   const int lane = threadIdx.x & 31;

@@ -757,8 +757,8 @@ def run_own(args):
                     torch.cuda.empty_cache()
             if "error" not in secondary.get("products_gs64_gaps", {"error": 1}):
                 secondary["products_gs64_gaps"]["note"] = (
-                    "products shape with 25 % of the dst rows isolated: the rows without edges are zero-filled inside the main "
-                    "kernel by the group that sees the jump in the sorted index (no memset of dst; the parity check covers the "
+                    "products shape with 25 % of the dst rows isolated: exactly the rows without edges are zeroed, by a small "
+                    "kernel that reads them off the cached plan's row pointer (no memset of dst; the parity check covers the "
                     "empty rows); compare with products_gs64")
 
     if rank != 0:

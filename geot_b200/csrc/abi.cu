@@ -582,9 +582,10 @@ int segment_reduce_impl(const void *src, const int64_t *src_index, const int64_t
   const bool ids_fit_32 = S <= 0xffffffffLL && (d_src != nullptr || E <= 0xffffffffLL);
 
   // Rows that receive no edge must read 0.  The kernels store every non-empty row exactly once; the rows in between
-  // are zero-filled INSIDE the main kernel by the group that sees the jump in the (sorted) index, so there is no
-  // memset of dst (the reference clears all of it first: csrc/gather_scatter.cpp:27-30).  Only a tail of rows beyond
-  // the largest index that the plan knows about is cleared here (normally empty: S = index[-1] + 1).
+  // are zeroed by zero_empty_rows_kernel when the call comes with a plan, else INSIDE the main kernel by the group that
+  // sees the jump in the (sorted) index -- either way there is no memset of dst (the reference clears all of it first:
+  // csrc/gather_scatter.cpp:27-30).  Only a tail of rows beyond the largest index that the plan knows about is cleared
+  // with a memset in the plan-less form (normally empty: S = index[-1] + 1).
   int zero_gaps = 0;
   int64_t fill_lo = ex.fill_lo, fill_hi = ex.fill_hi < 0 ? S : ex.fill_hi;
   if (ex.clear_mode == 0 && !accumulate && !(plan && !plan->has_gaps && plan->S == S)) {

@@ -5,7 +5,7 @@
 # legs: test (pytest -m gpu) | smoke | bench (default bench.py, own + reference arm) | benchN (torchrun bench at N = all
 #       visible GPUs, own + reference arm) | exch (N > 1: products / reddit with every exchange form) | model (configs[4]
 #       at N GPUs) | launches (ncu launch list of the default bench) | ncu:<workload> (one --set full capture) |
-#       tune:<workload>[:chunks] | timeline:<workload>[:exchange] (N > 1: where the step goes, CUDA-graph replay) |
+#       tune:<workload>[:chunks] | libs:<workload>:<lib,lib..>[:blocks] | ncut:<workload> | timeline:<workload>[:exchange] (N > 1: where the step goes, CUDA-graph replay) |
 #       sweep:<workload>[:rounds[:ctas]] (N > 1: exchange rounds x push grid) | compare (the reference's own CUDA kernels beside ours, sorted and sorted=False) |
 #       env:<NAME=VALUE> (exported for the legs that follow)
 TAG=$1; shift
@@ -64,6 +64,11 @@ PY
       tail -2 $OUT/sweep_$wl.err;;
     shards:*) IFS=: read -r _ wl parts <<< "$leg"
       timeout 300 python scripts/shard_probe.py $wl ${parts:-8} 2>&1 | grep -E "shard|rror" | tee -a $OUT/shard_probe.txt;;
+    libs:*) IFS=: read -r _ wl libs blocks <<< "$leg"      # same-process A/B of tuning builds (Makefile VARIANT=...)
+      timeout 300 python scripts/tune_libs.py $wl ${libs:-default} ${blocks:-1} 2>&1 | grep -E "lib=|rror" | tee -a $OUT/tune_libs.txt;;
+    ncut:*) IFS=: read -r _ wl <<< "$leg"      # one --set full capture of the timed-loop kernel, driven by the light tune script
+      timeout 240 ncu --set full --clock-control none --import-source on -k regex:segment_reduce_kernel -s 5 -c 1 -o $OUT/prof_$wl \
+        python scripts/tune.py $wl > $OUT/prof_$wl.log 2>&1; ls -la $OUT/prof_$wl.ncu-rep;;
     tune:*) IFS=: read -r _ wl chunks <<< "$leg"
       timeout 300 python scripts/tune.py $wl ${chunks:-0} 2>&1 | grep -E "lib=|rror" | tee -a $OUT/tune.txt;;
     *) echo "unknown leg $leg";;

@@ -181,7 +181,9 @@ constexpr int kHeadFlag = 128;
 constexpr int kHeadMax = 8;
 //   (A "lean register path" -- the same bookkeeping with the rows loaded straight into double-buffered registers, so
 //   that a gathered byte crosses the L1TEX data pipe once -- was built and measured in round 2: 15-25 % SLOWER than the
-//   ring on every gather workload, profiles/r02a_ring96_ab.txt; too few bytes in flight per SM.  Removed.)
+//   ring on every gather workload, profiles/r02a_ring96_ab.txt; too few bytes in flight per SM.  Removed.  So was a
+//   hybrid -- one or two rows of every ring sub-batch loaded straight into registers, the rest through cp.async: 18 % /
+//   42 % slower on Reddit gws, profiles/r02z_mix_ring_ab.txt.)
 template <typename T, int VECW, int LPR, int VPL, int PF_>
 struct ShapeOf {
   using A = typename AccOf<T>::type;

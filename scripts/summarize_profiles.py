@@ -150,9 +150,11 @@ def main():
     # bench.py looks the workload name up: map capture names prof_<x> -> workload names
     alias = {"prof_gws": "reddit_gws", "prof_reddit_gws": "reddit_gws", "prof_reddit_index_scatter": "reddit_index_scatter",
              "prof_products_gs64": "products_gs64", "prof_products_gs256": "products_gs256"}
-    for k, v in list(traffic.items()):
+    for k, v in sorted(traffic.items()):
         if k in alias:
             traffic[alias[k]] = v
+        elif k.startswith("prof_"):          # every other capture is named prof_<workload>
+            traffic[k[5:]] = v
     json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
     for fn in os.listdir(src):
         if fn.endswith((".json", ".jsonl", ".txt")) and os.path.getsize(os.path.join(src, fn)) < 200_000:

@@ -61,3 +61,31 @@ def test_power_law_graph_with_isolated_rows():
     assert 0.2 < frac < 0.3 and int(g.dst_index[-1]) == g.num_nodes - 1
     assert bool((g.dst_index[1:] >= g.dst_index[:-1]).all())
     assert int(torch.bincount(wl.power_law_graph("products", "cpu", scale=1 / 128).dst_index).min()) >= 1
+
+
+def test_every_default_bench_workload_has_an_ncu_traffic_figure():
+    """roofline.traffic / frac_dram of the default `bench.py` line and of its `secondary` entries come from
+    profiles/traffic.json (ncu dram bytes of the dominant kernel): no default workload may be left without one, and each
+    figure must lie between the compulsory and the logical bytes of its workload."""
+    import json
+    import os
+    import bench
+    import workloads as wl
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    traffic = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    shapes = {"reddit": (232_965, 114_615_892), "products": (2_449_029, 61_859_140), "arxiv": (169_343, 1_166_243)}
+    for name in ("reddit_gws", "reddit_index_scatter", "config1_index_scatter", "products_gs64", "products_gs64_gaps",
+                 "products_gs256", "arxiv_mh_spmm"):
+        assert name in traffic and traffic[name]["dram_bytes_per_launch"] > 0, name
+        assert bench.ncu_traffic(name) == traffic[name]["dram_bytes_per_launch"]
+        gname, op, F, H, dtype = bench.WORKLOADS[name]
+        es = 2 if "bf16" in str(dtype) or "float16" in str(dtype) else 4
+        if gname == "config1":
+            N, E, S = 0, 1_000_000, 50_000
+        else:
+            N, E = shapes[gname.split("+")[0]]
+            S = N
+        lo = wl.bytes_compulsory(op, E, S, N, F, H, es)
+        hi = wl.bytes_logical(op, E, S, N, F, H, es)
+        t = traffic[name]["dram_bytes_per_launch"]
+        assert 0.85 * lo <= t <= 1.05 * hi, (name, lo, t, hi)

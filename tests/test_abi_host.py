@@ -228,6 +228,12 @@ def test_reference_import_name_resolves():
         assert getattr(geot, name) is getattr(geot_b200, name), name
     from geot.match_replace import pattern_transform
     assert pattern_transform is geot_b200.pattern_transform
+    # the reference's other import paths (test/compile/*.py: `import geot.match_replace as replace`, `import geot.csr_gws`)
+    import geot.match_replace as replace
+    import geot.csr_gws            # noqa: F401  (a module in sys.modules; the attribute stays the operator, as in the reference)
+    from geot.gather_weight_scatter import gather_weight_scatter
+    assert replace.pattern_transform is geot_b200.pattern_transform and callable(geot.csr_gws)
+    assert gather_weight_scatter is geot_b200.gather_weight_scatter
 
 
 def test_mean_division_identity():
